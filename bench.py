@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py — parallel-map throughput of the kubetorch remote-map path on B200.
+
+Workload (BASELINE.json configs[1]): x → 2x over 64 Mi fp32 elements (256 MiB arg + 256 MiB result)
+sharded `x.chunk(N)` across N GPUs; a "step" is ONE remote call (scatter → exec → gather).
+
+  value   arg+result GB/s, device-timed, args/results resident in the root GPU's HBM
+          (N=1: one kernel on HBM; N>1: one process per GPU, each rank's kernel pulls its shard
+          from rank 0's arena over NVLink via CUDA IPC and pushes its result back — strong scaling)
+  e2e     the same metric through the public API (kt.fn(...).to(kt.Compute(gpus=N)) → remote(x))
+          with HOST buffers: every step copies the args host→device and the results device→host
+  roofline / cpu_baseline / clocks / gpu_launches: see the driver contract in DESIGN.md §Measurement.
+
+`--impl reference` times the reference's CPU dispatch path (oracle/ref_dispatch.OracleRuntime:
+pickle → base64 → JSON → one queue hop per rank → decode → run → encode → gather) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+N_ELEMS = 1 << 26  # 64 Mi fp32 = 256 MiB
+METRIC = "parallel_map_arg_plus_result_GBps"
+UNIT = "GB/s"
+REF_SAMPLE_ELEMS = 1 << 22  # 16 MiB per call for the CPU arm (64 MiB already takes ~7 s/call)
+
+
+def _peaks():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int = 0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._read, daemon=True)
+            self._t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                mhz = float(parts[1])
+                smax = float(parts[2])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(mhz)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than one sample: use the nearest samples
+            for ts, line in self.lines[-3:]:
+                parts = [p.strip() for p in line.split(",")]
+                try:
+                    sm.append(float(parts[1]))
+                    smax = float(parts[2])
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# =========================================================================================================
+# reference arm / cpu baseline
+# =========================================================================================================
+def time_reference(steps: int, warmup: int, n_ranks: int, n_elems: int = REF_SAMPLE_ELEMS):
+    """Calls/s and arg+result GB/s of the reference's CPU dispatch path on a bounded sample."""
+    import torch
+
+    from oracle.ref_dispatch import OracleRuntime
+
+    cores = os.cpu_count() or 1
+    n_ranks = max(1, min(n_ranks, cores))
+    x = torch.randn(n_elems, dtype=torch.float32)
+    with OracleRuntime("oracle.cases", "double", n_ranks, "spmd", extra_path=REPO) as rt:
+        for _ in range(max(1, warmup)):
+            out = rt.call(x, serialization="pickle")
+        assert torch.equal(torch.cat(out), x * 2)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            rt.call(x, serialization="pickle")
+        dt = time.perf_counter() - t0
+    bytes_per_call = 2 * n_elems * 4
+    return {
+        "value": bytes_per_call * steps / dt / 1e9,
+        "ms_per_step": dt / steps * 1e3,
+        "calls_per_sec": steps / dt,
+        "cores": min(cores, n_ranks + 2),  # client codec + coordinator + one per rank
+        "ranks": n_ranks,
+        "sample": f"x->2x over {n_elems} fp32 ({n_elems * 4 >> 20} MiB arg), {n_ranks} ranks, {steps} calls",
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = min(args.steps, 30)
+    r = time_reference(steps, min(args.warmup, 3), n_ranks=8)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "calls_per_sec": r["calls_per_sec"],
+        "config": {"workload": "parallel map x->2x, fp32, reference CPU dispatch (pickle/base64/JSON/queues), "
+                               "bounded sample of configs[1]", "sample": r["sample"]},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# =========================================================================================================
+# our arm
+# =========================================================================================================
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import kubetorch_b200 as kt
+    from kubetorch_b200.device import lib as L
+    from kubetorch_b200.device import ops
+    from oracle import cases
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a B200"
+    if world > 1:
+        assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    dev = local_rank if world > 1 else 0
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device(f"cuda:{dev}"))
+    n_gpus = world if world > 1 else args.gpus
+    K, W = args.steps, max(args.warmup, 3)
+    L.load()
+    ops.ensure_init([dev])
+    lib = L.load()
+    es = 4
+    nbytes = N_ELEMS * es
+
+    # ---- device-resident path -------------------------------------------------------------------------------
+    import ctypes
+
+    single_controller = (world == 1 and n_gpus > 1)
+    peer_ptr_x = peer_ptr_y = None
+    if world == 1:
+        devices = list(range(n_gpus))
+        ops.ensure_init(devices)
+        x = torch.randn(N_ELEMS, dtype=torch.float32, device="cuda:0")
+        y = torch.empty_like(x)
+
+        def one_call():
+            ops.scatter_map_gather(x, "scale", 2.0, 0.0, devices=devices, out_root=y)
+        launches_per_step = n_gpus
+    else:
+        # rank 0 owns the arg/result arenas; everyone maps them through CUDA IPC
+        handles = [None, None]
+        if rank == 0:
+            px, py = ctypes.c_void_p(), ctypes.c_void_p()
+            L.call("ktb_arena_alloc", dev, nbytes, ctypes.byref(px))
+            L.call("ktb_arena_alloc", dev, nbytes, ctypes.byref(py))
+            hx = (ctypes.c_ubyte * 64)()
+            hy = (ctypes.c_ubyte * 64)()
+            L.call("ktb_ipc_export", dev, px, hx)
+            L.call("ktb_ipc_export", dev, py, hy)
+            handles = [bytes(hx), bytes(hy)]
+            peer_ptr_x, peer_ptr_y = px.value, py.value
+            # fill x through a torch view of the arena
+            class _Arena:
+                def __init__(self, ptr, n):
+                    self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False),
+                                                     "version": 3}
+            x = torch.as_tensor(_Arena(px.value, N_ELEMS), device=f"cuda:{dev}")
+            y = torch.as_tensor(_Arena(py.value, N_ELEMS), device=f"cuda:{dev}")
+            x.normal_()
+            torch.cuda.synchronize()
+        dist.broadcast_object_list(handles, src=0)
+        if rank != 0:
+            px, py = ctypes.c_void_p(), ctypes.c_void_p()
+            hx = (ctypes.c_ubyte * 64).from_buffer_copy(handles[0])
+            hy = (ctypes.c_ubyte * 64).from_buffer_copy(handles[1])
+            L.call("ktb_ipc_open", dev, hx, ctypes.byref(px))
+            L.call("ktb_ipc_open", dev, hy, ctypes.byref(py))
+            peer_ptr_x, peer_ptr_y = px.value, py.value
+        b, e = ops.shard_bounds(N_ELEMS, world, rank)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+
+        def one_call():
+            L.call("ktb_map", dev, L.OP_SCALE, L.F32, peer_ptr_x + b * es, peer_ptr_y + b * es, e - b, 2.0, 0.0,
+                   L.VARIANT_AUTO, stream)
+        launches_per_step = 1  # per rank; N in total
+
+    def sync_all():
+        if world == 1:
+            for d in range(n_gpus):
+                torch.cuda.synchronize(d)
+        else:
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(W):
+        one_call()
+    sync_all()
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    sync_all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    ev0.record()
+    for _ in range(K):
+        one_call()
+    ev1.record()
+    sync_all()
+    t_wall1 = time.time()
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms_per_step = ms_total / K
+    value = 2 * nbytes / (ms_per_step * 1e-3) / 1e9
+
+    # parity spot-check of the timed result (full size, bit-exact: 2x is exact in fp32)
+    if rank == 0:
+        idx = torch.randint(0, N_ELEMS, (4096,), device=x.device)
+        assert torch.equal(y[idx], x[idx] * 2), "timed kernel produced wrong results"
+        assert torch.equal(y[-1024:], x[-1024:] * 2)
+
+    # ---- roofline of the dominant kernel (map_vec_kernel<F32,SCALE,256-bit>) --------------------------------
+    peak, peak_src = _peaks()
+    shard_bytes = nbytes if n_gpus == 1 else (ops.shard_bounds(N_ELEMS, n_gpus, 0)[1]) * es
+    if n_gpus == 1:
+        achieved = 2 * nbytes / (ms_per_step * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": _traffic(), "peak_source": peak_src, "kernel": "ktb::map_vec_kernel<F32,SCALE,32B>",
+                "algorithmic_bytes_per_launch": 2 * nbytes}
+    else:
+        # root NVLink port: (N-1)/N of the arg leaves and of the result enters the root, full duplex
+        link_bytes = (n_gpus - 1) * shard_bytes
+        achieved = link_bytes / (ms_per_step * 1e-3) / 1e9
+        roof = {"bound": "nvlink", "achieved": achieved, "peak": 770.0, "unit": "GB/s", "frac": achieved / 770.0,
+                "traffic": None, "peak_source": "measured peer copy per direction (B200_PROFILING.md)",
+                "kernel": "ktb::map_vec_kernel<F32,SCALE,32B> on peer pointers",
+                "algorithmic_bytes_per_launch": 2 * shard_bytes,
+                "note": "bytes crossing the root GPU's NVLink port per direction per call / step time"}
+
+    # ---- e2e: public API, host buffers ---------------------------------------------------------------------------
+    e2e = None
+    if rank == 0:
+        double = kt.mapped("scale", alpha=2.0)(cases.double)
+        remote = kt.fn(double, name="bench-double").to(
+            kt.Compute(gpus=n_gpus).distribute("b200", workers=1, num_proc=n_gpus))
+        xh = torch.randn(N_ELEMS, dtype=torch.float32).pin_memory()
+        e2e_steps = max(3, min(K, 10))
+        for _ in range(2):
+            out = remote(xh, serialization="pickle")
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            out = remote(xh, serialization="pickle")
+        dt = (time.perf_counter() - t0) / e2e_steps
+        assert torch.equal(torch.cat(out)[:4096], xh[:4096] * 2) and torch.equal(out[-1][-4096:], xh[-4096:] * 2)
+        e2e = {"value": 2 * nbytes / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": nbytes,
+               "d2h_bytes_per_step": nbytes, "ms_per_step": dt * 1e3, "steps": e2e_steps,
+               "path": "kt.fn(mapped).to(kt.Compute(gpus=N)) -> remote(pinned host tensor): per-rank chunked "
+                       "H2D/kernel/D2H over each GPU's own PCIe link, host-clock timed"}
+        remote.teardown()
+    if world > 1:
+        dist.barrier()
+
+    # ---- CPU baseline (N=1 only), bounded sample ---------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        r = time_reference(steps=5, warmup=1, n_ranks=8)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+               "calls_per_sec": r["calls_per_sec"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "calls_per_sec": 1e3 / ms_per_step,
+            "config": {
+                "workload": "configs[1]: parallel map x->2x over 64Mi fp32 (256 MiB arg + 256 MiB result), "
+                            f"x.chunk({n_gpus}) shards, args/results resident on GPU 0",
+                "n_elems": N_ELEMS, "parallelism": f"dp{n_gpus}",
+                "launch": "single controller" if world == 1 else "one process per GPU, CUDA-IPC peer arenas, "
+                          "calls pipelined per rank",
+                "l2": "inputs+outputs (512 MiB) exceed the 126 MB L2; no flush needed",
+            },
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": K * launches_per_step * (world if world > 1 else 1),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _traffic():
+    try:
+        with open(os.path.join(REPO, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,369 @@
+"""Tensor-facing wrappers over the C-ABI (torch.Tensor is the arg/result currency).
+
+Everything here enqueues hand-written sm_100a kernels from libktb200.so on the caller's current
+CUDA stream; nothing computes with torch ops.  Reference rows replaced:
+a3/a11/a12 (pack/unpack codecs), a7-a9 (fan-out / fan-in), a11 (callable execution for the
+registered ops).
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import lib as L
+
+_DTYPE_CODES = {
+    torch.uint8: L.U8,
+    torch.float32: L.F32,
+    torch.bfloat16: L.BF16,
+    torch.int32: L.I32,
+    torch.int64: L.I64,
+}
+OPS = {"identity": L.OP_IDENTITY, "scale": L.OP_SCALE, "affine": L.OP_AFFINE}
+
+_init_lock = threading.Lock()
+_registered: set = set()
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "kubetorch_b200 device path needs a CUDA device (B200, sm_100a); no CPU fallback exists. "
+            "Use kt.Compute(cpus=...) for the in-process CPU backend."
+        )
+
+
+def ensure_init(devices: Sequence[int]) -> None:
+    """Register devices with the library (enables NVLink peer access between all registered)."""
+    require_cuda()
+    devs = [int(d) for d in devices]
+    with _init_lock:
+        new = [d for d in devs if d not in _registered]
+        if not new:
+            return
+        L.call("ktb_init", len(new), L.arr(ctypes.c_int, new))
+        _registered.update(new)
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    try:
+        return _DTYPE_CODES[dtype]
+    except KeyError:
+        raise TypeError(f"kubetorch_b200 mapped ops support {sorted(str(k) for k in _DTYPE_CODES)}, got {dtype}")
+
+
+def _stream(device: int, stream: Optional[torch.cuda.Stream]) -> int:
+    s = stream if stream is not None else torch.cuda.current_stream(device)
+    return int(s.cuda_stream)
+
+
+def _check_dev_tensor(t: torch.Tensor, name: str) -> int:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t.device.index
+
+
+def row_elems(t: torch.Tensor) -> int:
+    """Elements per dim-0 row (the indivisible unit of `x.chunk(world)`)."""
+    if t.dim() == 0 or t.shape[0] == 0:
+        return 1
+    return max(1, t.numel() // t.shape[0])
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    b, e = ctypes.c_size_t(), ctypes.c_size_t()
+    L.call("ktb_shard_bounds", n, world, rank, ctypes.byref(b), ctypes.byref(e))
+    return b.value, e.value
+
+
+# ---- element-wise map ------------------------------------------------------------------------------
+def map_tensor(
+    x: torch.Tensor,
+    op: str = "identity",
+    alpha: float = 1.0,
+    beta: float = 0.0,
+    out: Optional[torch.Tensor] = None,
+    variant: int = L.VARIANT_AUTO,
+    stream: Optional[torch.cuda.Stream] = None,
+    device: Optional[int] = None,
+) -> torch.Tensor:
+    """out = op(x) on `device` (default: x's device). x/out may live on a peer GPU."""
+    xd = _check_dev_tensor(x, "x")
+    dev = xd if device is None else int(device)
+    ensure_init({dev, xd})
+    if out is None:
+        with torch.cuda.device(dev):
+            out = torch.empty_like(x, device=f"cuda:{dev}")
+    else:
+        od = _check_dev_tensor(out, "out")
+        ensure_init({od})
+        if out.dtype != x.dtype or out.numel() != x.numel():
+            raise ValueError("out must match x in dtype and numel")
+    L.call(
+        "ktb_map", dev, OPS[op], dtype_code(x.dtype), x.data_ptr(), out.data_ptr(), x.numel(),
+        float(alpha), float(beta), int(variant), _stream(dev, stream),
+    )
+    return out
+
+
+_ws_cache = {}
+
+
+def _workspace(dev: int) -> torch.Tensor:
+    key = (dev, int(torch.cuda.current_stream(dev).cuda_stream))
+    ws = _ws_cache.get(key)
+    if ws is None:
+        nbytes = L.load().ktb_reduce_workspace_bytes()
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=f"cuda:{dev}")
+        _ws_cache[key] = ws
+    return ws
+
+
+def acc_dtype(dtype: torch.dtype) -> torch.dtype:
+    return torch.float32 if dtype in (torch.float32, torch.bfloat16) else torch.int64
+
+
+def map_reduce_sum(
+    x: torch.Tensor,
+    op: str = "identity",
+    alpha: float = 1.0,
+    beta: float = 0.0,
+    out: Optional[torch.Tensor] = None,
+    stream: Optional[torch.cuda.Stream] = None,
+    device: Optional[int] = None,
+) -> torch.Tensor:
+    """out[0] = sum(op(x)); fp32 accumulator for f32/bf16, int64 for integer dtypes."""
+    xd = _check_dev_tensor(x, "x")
+    dev = xd if device is None else int(device)
+    ensure_init({dev, xd})
+    if x.dtype == torch.uint8:
+        raise TypeError("uint8 is not reducible")
+    if out is None:
+        out = torch.empty(1, dtype=acc_dtype(x.dtype), device=f"cuda:{dev}")
+    L.call(
+        "ktb_map_reduce_sum", dev, OPS[op], dtype_code(x.dtype), x.data_ptr(), x.numel(), float(alpha),
+        float(beta), out.data_ptr(), _workspace(dev).data_ptr(), _stream(dev, stream),
+    )
+    return out
+
+
+# ---- pack / unpack ---------------------------------------------------------------------------------
+def pack_layout(nbytes: Sequence[int]) -> Tuple[List[int], int]:
+    n = len(nbytes)
+    offs = (ctypes.c_size_t * max(n, 1))()
+    total = ctypes.c_size_t()
+    L.call("ktb_pack_layout", L.arr(ctypes.c_size_t, list(nbytes)) if n else None, n, offs, ctypes.byref(total))
+    return [offs[i] for i in range(n)], total.value
+
+
+def pack(
+    tensors: Sequence[torch.Tensor],
+    arena: Optional[torch.Tensor] = None,
+    stream: Optional[torch.cuda.Stream] = None,
+) -> Tuple[torch.Tensor, List[int]]:
+    """Gather tensor leaves into one uint8 arena at 256-byte aligned offsets. Returns (arena, offsets)."""
+    if not tensors:
+        return (arena if arena is not None else torch.empty(0, dtype=torch.uint8)), []
+    dev = _check_dev_tensor(tensors[0], "tensors[0]")
+    for i, t in enumerate(tensors):
+        if _check_dev_tensor(t, f"tensors[{i}]") != dev:
+            raise ValueError("all tensors to pack must be on the same device")
+    ensure_init({dev})
+    nbytes = [t.numel() * t.element_size() for t in tensors]
+    offsets, total = pack_layout(nbytes)
+    if arena is None:
+        arena = torch.empty(max(total, 1), dtype=torch.uint8, device=f"cuda:{dev}")
+    elif arena.numel() * arena.element_size() < total:
+        raise ValueError(f"arena too small: need {total} bytes")
+    n = len(tensors)
+    c_offs = L.arr(ctypes.c_size_t, offsets)
+    L.call(
+        "ktb_pack", dev, L.arr(ctypes.c_void_p, [t.data_ptr() for t in tensors]), L.arr(ctypes.c_size_t, nbytes), n,
+        arena.data_ptr(), arena.numel() * arena.element_size(), c_offs, 0, _stream(dev, stream),
+    )
+    return arena, offsets
+
+
+def unpack(
+    arena: torch.Tensor,
+    offsets: Sequence[int],
+    outs: Sequence[torch.Tensor],
+    stream: Optional[torch.cuda.Stream] = None,
+) -> Sequence[torch.Tensor]:
+    """Scatter arena segments back into the destination tensors `outs` (same device as arena)."""
+    if not outs:
+        return outs
+    dev = _check_dev_tensor(arena, "arena")
+    ensure_init({dev})
+    nbytes = [t.numel() * t.element_size() for t in outs]
+    for i, t in enumerate(outs):
+        _check_dev_tensor(t, f"outs[{i}]")
+    L.call(
+        "ktb_unpack", dev, arena.data_ptr(), L.arr(ctypes.c_size_t, list(offsets)), L.arr(ctypes.c_size_t, nbytes),
+        len(outs), L.arr(ctypes.c_void_p, [t.data_ptr() for t in outs]), _stream(dev, stream),
+    )
+    return outs
+
+
+def arena_views(arena: torch.Tensor, offsets: Sequence[int], specs: Sequence[Tuple[torch.dtype, Tuple[int, ...]]]):
+    """Zero-copy typed views of packed segments (offsets are 256-byte aligned)."""
+    flat = arena.view(torch.uint8).reshape(-1)
+    views = []
+    for off, (dtype, shape) in zip(offsets, specs):
+        n = 1
+        for s in shape:
+            n *= s
+        nb = n * torch.empty((), dtype=dtype).element_size()
+        views.append(flat[off : off + nb].view(dtype).reshape(shape))
+    return views
+
+
+def map_batch(
+    xs: Sequence[torch.Tensor],
+    op: str = "identity",
+    alpha: float = 1.0,
+    beta: float = 0.0,
+    outs: Optional[Sequence[torch.Tensor]] = None,
+    stream: Optional[torch.cuda.Stream] = None,
+) -> Sequence[torch.Tensor]:
+    """n independent small calls out_i = op(x_i) coalesced into one segmented launch."""
+    if not xs:
+        return []
+    dev = _check_dev_tensor(xs[0], "xs[0]")
+    ensure_init({dev})
+    dt = xs[0].dtype
+    for i, t in enumerate(xs):
+        _check_dev_tensor(t, f"xs[{i}]")
+        if t.dtype != dt:
+            raise ValueError("map_batch needs one dtype per batch")
+    if outs is None:
+        outs = [torch.empty_like(t) for t in xs]
+    L.call(
+        "ktb_map_batch", dev, OPS[op], dtype_code(dt), L.arr(ctypes.c_void_p, [t.data_ptr() for t in xs]),
+        L.arr(ctypes.c_void_p, [t.data_ptr() for t in outs]), L.arr(ctypes.c_size_t, [t.numel() for t in xs]),
+        len(xs), float(alpha), float(beta), _stream(dev, stream),
+    )
+    return outs
+
+
+# ---- multi-GPU ---------------------------------------------------------------------------------------
+def broadcast(src: torch.Tensor, dsts: Sequence[torch.Tensor], stream: Optional[torch.cuda.Stream] = None):
+    """One kernel on src's device reads src once and peer-stores it to every dst."""
+    root = _check_dev_tensor(src, "src")
+    devs = {root}
+    nbytes = src.numel() * src.element_size()
+    for i, d in enumerate(dsts):
+        devs.add(_check_dev_tensor(d, f"dsts[{i}]"))
+        if d.numel() * d.element_size() < nbytes:
+            raise ValueError(f"dsts[{i}] is smaller than src")
+    ensure_init(devs)
+    L.call(
+        "ktb_broadcast", root, src.data_ptr(), L.arr(ctypes.c_void_p, [d.data_ptr() for d in dsts]), len(dsts),
+        nbytes, _stream(root, stream),
+    )
+    return dsts
+
+
+def scatter_map_gather(
+    x_root: torch.Tensor,
+    op: str,
+    alpha: float = 1.0,
+    beta: float = 0.0,
+    devices: Sequence[int] = (0,),
+    out_root: Optional[torch.Tensor] = None,
+    root_rank: int = 0,
+    variant: int = L.VARIANT_AUTO,
+    granule: Optional[int] = None,
+) -> torch.Tensor:
+    """Fused scatter → map → gather: rank r's kernel pulls shard r of x_root (`x.chunk(world)` along
+    dim 0; `granule` = elements per row, default from x_root's shape) from the root GPU over NVLink,
+    applies op, and pushes it into out_root."""
+    root = _check_dev_tensor(x_root, "x_root")
+    devs = [int(d) for d in devices]
+    if devs[root_rank] != root:
+        raise ValueError(f"x_root lives on cuda:{root} but devices[{root_rank}] is {devs[root_rank]}")
+    ensure_init(set(devs))
+    if out_root is None:
+        out_root = torch.empty_like(x_root)
+    streams = [int(torch.cuda.current_stream(d).cuda_stream) for d in devs]
+    L.call(
+        "ktb_scatter_map_gather", OPS[op], dtype_code(x_root.dtype), x_root.data_ptr(), out_root.data_ptr(),
+        x_root.numel(), int(granule or row_elems(x_root)), float(alpha), float(beta), len(devs), L.arr(ctypes.c_int, devs), root_rank, int(variant),
+        L.arr(L.c_uintptr, streams),
+    )
+    return out_root
+
+
+def scatter_map_reduce(
+    x_root: torch.Tensor,
+    op: str,
+    alpha: float = 1.0,
+    beta: float = 0.0,
+    devices: Sequence[int] = (0,),
+    root_rank: int = 0,
+    granule: Optional[int] = None,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Gather-reduce variant. Returns (total[1], partials[n_ranks]) on the root GPU."""
+    root = _check_dev_tensor(x_root, "x_root")
+    devs = [int(d) for d in devices]
+    if devs[root_rank] != root:
+        raise ValueError(f"x_root lives on cuda:{root} but devices[{root_rank}] is {devs[root_rank]}")
+    ensure_init(set(devs))
+    adt = acc_dtype(x_root.dtype)
+    partials = torch.zeros(len(devs), dtype=adt, device=x_root.device)
+    total = torch.empty(1, dtype=adt, device=x_root.device)
+    wss = [_workspace(d) for d in devs]
+    streams = [int(torch.cuda.current_stream(d).cuda_stream) for d in devs]
+    L.call(
+        "ktb_scatter_map_reduce", OPS[op], dtype_code(x_root.dtype), x_root.data_ptr(), x_root.numel(),
+        int(granule or row_elems(x_root)), float(alpha),
+        float(beta), len(devs), L.arr(ctypes.c_int, devs), root_rank, partials.data_ptr(), total.data_ptr(),
+        L.arr(ctypes.c_void_p, [w.data_ptr() for w in wss]), L.arr(L.c_uintptr, streams),
+    )
+    return total, partials
+
+
+# ---- host-resident args ------------------------------------------------------------------------------
+_stage_cache = {}
+
+
+def map_host(
+    x_host: torch.Tensor,
+    op: str = "identity",
+    alpha: float = 1.0,
+    beta: float = 0.0,
+    out_host: Optional[torch.Tensor] = None,
+    device: int = 0,
+    chunk_bytes: int = 8 << 20,
+) -> torch.Tensor:
+    """out_host = op(x_host), both pinned host tensors; H2D, kernel and D2H of successive chunks overlap."""
+    require_cuda()
+    if x_host.is_cuda or not x_host.is_pinned():
+        raise ValueError("x_host must be a pinned host tensor")
+    if out_host is None:
+        out_host = torch.empty_like(x_host).pin_memory()
+    elif out_host.is_cuda or not out_host.is_pinned():
+        raise ValueError("out_host must be a pinned host tensor")
+    ensure_init({device})
+    key = (device, chunk_bytes)
+    st = _stage_cache.get(key)
+    if st is None:
+        st = (
+            torch.empty(2 * chunk_bytes, dtype=torch.uint8, device=f"cuda:{device}"),
+            torch.empty(2 * chunk_bytes, dtype=torch.uint8, device=f"cuda:{device}"),
+        )
+        _stage_cache[key] = st
+    L.call(
+        "ktb_map_host", device, OPS[op], dtype_code(x_host.dtype), x_host.data_ptr(), out_host.data_ptr(),
+        x_host.numel(), float(alpha), float(beta), chunk_bytes, st[0].data_ptr(), st[1].data_ptr(),
+    )
+    return out_host
+
+
+def set_tuning(key: int, value: int) -> None:
+    L.call("ktb_set_tuning", key, value)

@@ -1,0 +1,136 @@
+"""Rank worker process: loads the user callable once, then serves calls.
+
+Role of kt/serving/process_worker.py:15-272 (ProcessWorker) on the local route, re-designed:
+  * requests arrive on a duplex multiprocessing Connection as raw bytes — ONE pickle of the call
+    payload made by the coordinator is shared by all ranks (the reference re-pickles the whole
+    base64 body once per rank through mp.Queue, process_pool.py:149-161, its largest cost);
+  * no 10 ms queue poll (process_worker.py:198-202): the worker blocks in recv_bytes();
+  * sync callables run on a thread pool (max_threads, default 10 under SPMD like
+    execution_supervisor.py:39), async callables on one asyncio loop, so concurrent calls overlap
+    exactly as in the reference (kt/serving/design.md:67-85);
+  * per-request env update with the distributed contract (process_worker.py:75-102,128-129).
+"""
+from __future__ import annotations
+
+import asyncio
+import importlib
+import inspect
+import json
+import os
+import pickle
+import sys
+import threading
+from concurrent.futures import ThreadPoolExecutor
+from typing import Any, Dict, Optional
+
+from ..exceptions import SerializationError
+from .codec import check_allowed, package_exception
+
+SHUTDOWN = b"__KTB_SHUTDOWN__"
+
+
+def load_callable(pointers, init_args: Optional[dict]):
+    """Import (root_path, module_name, name) — the reference's pointer triple — and instantiate classes."""
+    root_path, module_name, name = pointers
+    if root_path and root_path not in sys.path:
+        sys.path.insert(0, root_path)
+    module = importlib.import_module(module_name)
+    obj = module
+    for part in name.split("."):
+        obj = getattr(obj, part)
+    return instantiate(obj, init_args)
+
+
+def instantiate(obj, init_args: Optional[dict]):
+    """Classes become one instance per rank built from init_args (http_server.py:1088-1101)."""
+    if inspect.isclass(obj):
+        obj = obj(**dict(init_args or {}))
+    return obj
+
+
+def resolve_method(callable_obj, cls_or_fn_name: str, method_name: Optional[str]):
+    from .codec import HTTPException
+
+    if method_name:
+        if not hasattr(callable_obj, method_name):
+            raise HTTPException(404, f"Method '{method_name}' not found in class '{cls_or_fn_name}'")
+        return getattr(callable_obj, method_name)
+    return callable_obj
+
+
+def validate_result(result: Any, serialization: str):
+    if serialization == "json":
+        try:
+            json.dumps(result)
+        except (TypeError, ValueError) as e:
+            raise SerializationError(f"Result could not be serialized to JSON: {e}")
+    return result
+
+
+def worker_main(conn, local_rank: int, pointers, init_args, name: str, max_threads: int, base_env: Dict[str, str],
+                allowed_serialization: str):
+    os.environ["LOCAL_RANK"] = str(local_rank)  # also set at construction in the reference (process_worker.py:33)
+    os.environ.update(base_env)
+    send_lock = threading.Lock()
+
+    def reply(msg: dict):
+        data = pickle.dumps(msg, protocol=5)
+        with send_lock:
+            conn.send_bytes(data)
+
+    try:
+        callable_obj = load_callable(pointers, init_args)
+    except BaseException as e:  # noqa: BLE001
+        reply({"id": -1, "ok": False, "envelope": package_exception(e)})
+        return
+    reply({"id": -1, "ok": True, "result": None})
+
+    executor = ThreadPoolExecutor(max_workers=max_threads, thread_name_prefix=f"ktb-rank{local_rank}")
+    loop = asyncio.new_event_loop()
+    loop_thread = threading.Thread(target=loop.run_forever, name="ktb-asyncio", daemon=True)
+    loop_thread.start()
+
+    def run_request(req: dict):
+        try:
+            os.environ.update(req.get("env") or {})
+            check_allowed(req["serialization"], allowed_serialization)
+            args, kwargs = pickle.loads(req["payload"])
+            method = resolve_method(callable_obj, name, req.get("method"))
+            if inspect.iscoroutinefunction(method):
+                result = asyncio.run_coroutine_threadsafe(method(*args, **kwargs), loop).result()
+            else:
+                result = method(*args, **kwargs)
+                if inspect.isawaitable(result):
+                    async def _await(x):
+                        return await x
+                    result = asyncio.run_coroutine_threadsafe(_await(result), loop).result()
+            validate_result(result, req["serialization"])
+            try:
+                payload = pickle.dumps(result, protocol=5)
+            except Exception as e:  # noqa: BLE001
+                raise SerializationError(f"Result could not be serialized with pickle: {e}")
+            reply({"id": req["id"], "ok": True, "result": payload})
+        except BaseException as e:  # noqa: BLE001
+            reply({"id": req["id"], "ok": False, "envelope": package_exception(e)})
+
+    while True:
+        try:
+            data = conn.recv_bytes()
+        except (EOFError, OSError):
+            break
+        if data == SHUTDOWN:
+            break
+        req = pickle.loads(data)
+        executor.submit(run_request, req)
+
+    executor.shutdown(wait=False, cancel_futures=True)
+    loop.call_soon_threadsafe(loop.stop)
+    # framework cleanup on reload (kt/serving/spmd/pytorch_process.py:8-16)
+    try:
+        if "torch.distributed" in sys.modules:
+            import torch.distributed as dist
+
+            if dist.is_initialized():
+                dist.destroy_process_group()
+    except Exception:  # noqa: BLE001
+        pass

@@ -1,0 +1,108 @@
+"""User callables of the parity cases, written exactly as a kubetorch user writes SPMD functions:
+they read RANK / WORLD_SIZE from the environment the reference's worker sets
+(kt/serving/process_worker.py:75-102,128-129) and shard their own input.
+
+TEST INFRASTRUCTURE.  These functions are the *semantic definition* of the registered device
+ops: the reference runtime (oracle/make_golden.py) and the oracle restatement
+(oracle/ref_dispatch.py) execute them on CPU; the CUDA path must reproduce their results.
+"""
+import os
+
+
+def _rank_world():
+    return int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+
+
+def _shard(x):
+    """`x.chunk(WORLD_SIZE)[RANK]` with the empty shard torch.chunk omits for ranks past the data."""
+    r, w = _rank_world()
+    chunks = x.chunk(w)  # along dim 0
+    return chunks[r] if r < len(chunks) else x[:0]
+
+
+# ---- reference test assets restated (tests/assets/*/.py) -------------------------------------------
+def summer(a, b):
+    return a + b
+
+
+def torch_summer(a, b):
+    import torch
+
+    return int(torch.sum(torch.tensor([a, b])))
+
+
+async def async_summer(a, b, sleep_time=0.01, return_times=False):
+    import asyncio
+
+    await asyncio.sleep(sleep_time)
+    return a + b
+
+
+def hello_world():
+    return "Hello from Kubetorch!"
+
+
+class Number:
+    def __init__(self, size=5):
+        self.size = size
+        self.calls = 0
+
+    def add(self, x, y):
+        self.calls += 1
+        return x + y
+
+    def count(self):
+        return self.calls
+
+
+def env_report():
+    keys = ["WORLD_SIZE", "RANK", "LOCAL_RANK", "NODE_RANK", "POD_IPS", "MASTER_ADDR", "MASTER_PORT"]
+    return {k: os.environ.get(k) for k in keys}
+
+
+def raise_value_error(msg):
+    raise ValueError(msg)
+
+
+# ---- mapped-callable semantics (BASELINE configs C2 / C5 and variants) ------------------------------
+def identity(x):
+    return _shard(x)
+
+
+def double(x):
+    return _shard(x) * 2
+
+
+def scale(x, alpha):
+    return _shard(x) * alpha
+
+
+def affine(x, alpha, beta):
+    return _shard(x) * alpha + beta
+
+
+def shard_sum(x, alpha=1, beta=0):
+    """Gather-reduce variant: each rank returns the sum of its mapped shard."""
+    import torch
+
+    y = _shard(x) * alpha + beta if (alpha != 1 or beta != 0) else _shard(x)
+    if y.dtype in (torch.float32, torch.bfloat16):
+        return float(y.float().sum())
+    return int(y.sum())
+
+
+def spmd_identity(x):
+    """Reference broadcast semantics: every rank sees (and returns) the full argument."""
+    return x
+
+
+def mlp_policy(obs, w1, w2, w3):
+    """bf16 MLP policy of BASELINE config C4 on this rank's shard of observations (rows)."""
+    import torch
+
+    r, w = _rank_world()
+    rows = obs.chunk(w, dim=0)
+    o = rows[r] if r < len(rows) else obs[:0]
+    h = torch.relu(o @ w1.t())
+    h = torch.relu(h @ w2.t())
+    return h @ w3.t()

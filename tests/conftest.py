@@ -1,0 +1,32 @@
+import os
+import sys
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+# spawned rank processes import the user modules (oracle.cases, tests.*) by name
+os.environ["PYTHONPATH"] = os.pathsep.join([REPO] + [p for p in os.environ.get("PYTHONPATH", "").split(os.pathsep) if p])
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import torch
+
+    from oracle.golden_inputs import make_inputs, tensor_sha256
+
+    fx = torch.load(os.path.join(REPO, "tests", "golden", "ref_runtime.pt"), weights_only=False)
+    inputs = make_inputs()
+    for k, v in inputs.items():  # regenerated inputs must be the tensors the reference saw
+        assert tensor_sha256(v) == fx["input_sha256"][k], f"golden input {k} does not regenerate bit-exactly"
+    fx["all_inputs"] = inputs
+    return fx
+
+
+def resolve_args(fx, arg_spec):
+    return [fx["all_inputs"][a[1:]] if isinstance(a, str) and a.startswith("@") else a for a in arg_spec]
