@@ -171,7 +171,7 @@ int ktb_broadcast(int root, const void* src, void* const* dsts, int n_dst, size_
  * rank r (device devs[r]) pulls its torch.chunk shard of src_root straight out of the root
  * GPU's memory, applies op, and pushes the result into dst_root at the same offset.  No
  * staging copies: root HBM is read once and written once.  streams[r] is the stream on
- * devs[r] (may be NULL → library streams).  The call is ordered after prior work on
+ * devs[r], used verbatim (0 = legacy default stream); streams == NULL → library-owned streams.  The call is ordered after prior work on
  * streams[root_rank] and that stream is ordered after all ranks' work on return.
  * `granule` = elements per indivisible unit (a dim-0 row): shards are ktb_shard_bounds over
  * n_elems/granule units, i.e. exactly `x.chunk(world)` along dim 0; n_elems % granule must be 0. */

@@ -136,9 +136,9 @@ int ktb_scatter_map_gather(int op, int dtype, const void* src_root, void* dst_ro
   const MapParams p = make_params(alpha, beta);
   const int root_dev = devs[root_rank];
   DeviceInfo* root = device_info(root_dev);
+  // streams == NULL → library streams; otherwise streams[r] verbatim (0 is the legacy default stream)
   auto stream_of = [&](int r) {
-    return (streams && streams[r]) ? reinterpret_cast<cudaStream_t>(streams[r])
-                                   : device_info(devs[r])->stream_rank;
+    return streams ? reinterpret_cast<cudaStream_t>(streams[r]) : device_info(devs[r])->stream_rank;
   };
   cudaStream_t root_stream = stream_of(root_rank);
   {
@@ -184,9 +184,9 @@ int ktb_scatter_map_reduce(int op, int dtype, const void* src_root, size_t n_ele
   const size_t acc_size = (dtype == KTB_F32 || dtype == KTB_BF16) ? 4 : 8;
   const int root_dev = devs[root_rank];
   DeviceInfo* root = device_info(root_dev);
+  // streams == NULL → library streams; otherwise streams[r] verbatim (0 is the legacy default stream)
   auto stream_of = [&](int r) {
-    return (streams && streams[r]) ? reinterpret_cast<cudaStream_t>(streams[r])
-                                   : device_info(devs[r])->stream_rank;
+    return streams ? reinterpret_cast<cudaStream_t>(streams[r]) : device_info(devs[r])->stream_rank;
   };
   cudaStream_t root_stream = stream_of(root_rank);
   {

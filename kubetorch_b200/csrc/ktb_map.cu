@@ -24,19 +24,32 @@ static std::atomic<int> g_vec_ctas_per_sm{4};
 static std::atomic<int> g_tma_ctas_per_sm{1};
 static std::atomic<int> g_tma_cfg{0};       // 0: 4 x 32 KiB stages, 1: 6 x 32 KiB, 2: 8 x 16 KiB (2 CTA/SM)
 static std::atomic<int> g_auto_variant{KTB_VARIANT_VEC};
+static std::atomic<int> g_vec_flavor{0};    // cache flavor (experiments: F32-scale and identity only)
+static std::atomic<int> g_vec_unroll{4};    // 2 | 4 | 8 (experiments: same kernels)
 
 constexpr int kVecThreads = 256;
 constexpr int kVecUnroll = 4;
 
 // ---- VEC -----------------------------------------------------------------------------------------
-template <int VB>
+// FL (cache flavor, 256-bit path only): 0 = L1::no_allocate, 1 = default caching,
+// 2 = L1::no_allocate + L2::evict_first on loads and stores, 3 = evict_first loads only.
+template <int VB, int FL>
 __device__ __forceinline__ void ld_vec(const uint8_t* p, uint32_t (&w)[VB / 4]) {
   if constexpr (VB == 32) {
-    asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]),
-                   "=r"(w[6]), "=r"(w[7])
-                 : "l"(p)
-                 : "memory");
+#define KTB_LD256(MOD)                                                                          \
+  asm volatile("ld.global" MOD ".v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                       \
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]),        \
+                 "=r"(w[6]), "=r"(w[7])                                                         \
+               : "l"(p)                                                                         \
+               : "memory")
+    if constexpr (FL == 1) {
+      KTB_LD256("");
+    } else if constexpr (FL == 2 || FL == 3) {
+      KTB_LD256(".L1::no_allocate.L2::evict_first");
+    } else {
+      KTB_LD256(".L1::no_allocate");
+    }
+#undef KTB_LD256
   } else {
     asm volatile("ld.global.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
@@ -44,19 +57,31 @@ __device__ __forceinline__ void ld_vec(const uint8_t* p, uint32_t (&w)[VB / 4]) 
                  : "memory");
   }
 }
-template <int VB>
+template <int VB, int FL>
 __device__ __forceinline__ void st_vec(uint8_t* p, const uint32_t (&w)[VB / 4]) {
   if constexpr (VB == 32) {
-    stg256(p, w);
+#define KTB_ST256(MOD)                                                                          \
+  asm volatile("st.global" MOD ".v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]),  \
+               "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])      \
+               : "memory")
+    if constexpr (FL == 1) {
+      KTB_ST256("");
+    } else if constexpr (FL == 2) {
+      KTB_ST256(".L1::no_allocate.L2::evict_first");
+    } else {
+      KTB_ST256(".L1::no_allocate");
+    }
+#undef KTB_ST256
   } else {
     stg128(p, w);
   }
 }
 
-template <int DT, int OP, int VB>
+template <int DT, int OP, int VB, int FL = 0, int UNROLL = kVecUnroll>
 __global__ void __launch_bounds__(kVecThreads)
     map_vec_kernel(const uint8_t* src, uint8_t* dst, size_t n_bytes, MapParams p) {
   constexpr int NW = VB / 4;
+  constexpr int kVecUnroll = UNROLL;
   constexpr size_t TILE = (size_t)kVecThreads * kVecUnroll * VB;  // bytes per CTA iteration
   constexpr size_t ROW = (size_t)kVecThreads * VB;                // bytes per unrolled step
   const size_t n_full = n_bytes / TILE;
@@ -65,11 +90,11 @@ __global__ void __launch_bounds__(kVecThreads)
     const size_t off = t * TILE + (size_t)threadIdx.x * VB;
     uint32_t w[kVecUnroll][NW];
 #pragma unroll
-    for (int j = 0; j < kVecUnroll; ++j) ld_vec<VB>(src + off + j * ROW, w[j]);
+    for (int j = 0; j < kVecUnroll; ++j) ld_vec<VB, FL>(src + off + j * ROW, w[j]);
 #pragma unroll
     for (int j = 0; j < kVecUnroll; ++j) {
       apply_words<DT, OP, NW>(w[j], p);
-      st_vec<VB>(dst + off + j * ROW, w[j]);
+      st_vec<VB, FL>(dst + off + j * ROW, w[j]);
     }
   }
 
@@ -79,9 +104,9 @@ __global__ void __launch_bounds__(kVecThreads)
     const size_t n_vec = (n_bytes - base) / VB;
     for (size_t v = threadIdx.x; v < n_vec; v += kVecThreads) {
       uint32_t w[NW];
-      ld_vec<VB>(src + base + v * VB, w);
+      ld_vec<VB, FL>(src + base + v * VB, w);
       apply_words<DT, OP, NW>(w, p);
-      st_vec<VB>(dst + base + v * VB, w);
+      st_vec<VB, FL>(dst + base + v * VB, w);
     }
     constexpr size_t ES = (DT == KTB_U8) ? 1 : (DT == KTB_BF16 ? 2 : (DT == KTB_I64 ? 8 : 4));
     const size_t tail = base + n_vec * VB;
@@ -203,17 +228,37 @@ static int launch_typed(int dev, const uint8_t* src, uint8_t* dst, size_t n_elem
   if (variant == KTB_VARIANT_VEC && (both & 15)) variant = KTB_VARIANT_SCALAR;
 
   if (variant == KTB_VARIANT_VEC) {
-    const int ctas = di->sm_count * std::max(1, g_vec_ctas_per_sm.load());
+    // ctas_per_sm == 0 → one tile per CTA (the hardware scheduler balances the tail);
+    // otherwise a persistent grid of sm_count * ctas_per_sm CTAs striding over tiles.
+    const int per_sm = g_vec_ctas_per_sm.load();
+    auto grid_for = [&](size_t tile_bytes) {
+      size_t tiles = std::max<size_t>(n_bytes / tile_bytes, 1);
+      if (per_sm <= 0) return (int)std::min<size_t>(tiles, 0x7fffffffULL);
+      return (int)std::min<size_t>(tiles, (size_t)di->sm_count * per_sm);
+    };
     if ((both & 31) == 0) {
-      constexpr size_t TILE = (size_t)kVecThreads * kVecUnroll * 32;
-      size_t tiles = n_bytes / TILE;
-      int grid = (int)std::min<size_t>(std::max<size_t>(tiles, 1), (size_t)ctas);
-      map_vec_kernel<DT, OP, 32><<<grid, kVecThreads, 0, stream>>>(src, dst, n_bytes, p);
+      constexpr bool kTunable = (DT == KTB_U8) || (DT == KTB_F32 && OP == KTB_OP_SCALE);
+      const int fl = kTunable ? g_vec_flavor.load() : 0;
+      const int un = kTunable ? g_vec_unroll.load() : 4;
+#define KTB_VEC32(FL, UN)                                                                          \
+  map_vec_kernel<DT, OP, 32, FL, UN>                                                               \
+      <<<grid_for((size_t)kVecThreads * (UN)*32), kVecThreads, 0, stream>>>(src, dst, n_bytes, p)
+      if constexpr (kTunable) {
+        if (un == 2) {
+          if (fl == 1) KTB_VEC32(1, 2); else if (fl == 2) KTB_VEC32(2, 2); else if (fl == 3) KTB_VEC32(3, 2); else KTB_VEC32(0, 2);
+        } else if (un == 8) {
+          if (fl == 1) KTB_VEC32(1, 8); else if (fl == 2) KTB_VEC32(2, 8); else if (fl == 3) KTB_VEC32(3, 8); else KTB_VEC32(0, 8);
+        } else {
+          if (fl == 1) KTB_VEC32(1, 4); else if (fl == 2) KTB_VEC32(2, 4); else if (fl == 3) KTB_VEC32(3, 4); else KTB_VEC32(0, 4);
+        }
+      } else {
+        (void)fl; (void)un;
+        KTB_VEC32(0, 4);
+      }
+#undef KTB_VEC32
     } else {
-      constexpr size_t TILE = (size_t)kVecThreads * kVecUnroll * 16;
-      size_t tiles = n_bytes / TILE;
-      int grid = (int)std::min<size_t>(std::max<size_t>(tiles, 1), (size_t)ctas);
-      map_vec_kernel<DT, OP, 16><<<grid, kVecThreads, 0, stream>>>(src, dst, n_bytes, p);
+      map_vec_kernel<DT, OP, 16>
+          <<<grid_for((size_t)kVecThreads * kVecUnroll * 16), kVecThreads, 0, stream>>>(src, dst, n_bytes, p);
     }
   } else if (variant == KTB_VARIANT_TMA) {
     const int cfg = g_tma_cfg.load();
@@ -297,12 +342,15 @@ using namespace ktb;
 extern "C" {
 
 // Experiment knobs (not part of the stable ABI; used by the bench sweep).
-//   key 0: VEC CTAs per SM   key 1: TMA CTAs per SM   key 2: TMA stage config   key 3: AUTO variant
+//   key 0: VEC CTAs per SM (0 = one tile per CTA)   key 1: TMA CTAs per SM   key 2: TMA stage config
+//   key 3: AUTO variant   key 4: VEC cache flavor   key 5: VEC unroll
 int ktb_set_tuning(int key, int value) {
   switch (key) {
     case 0: g_vec_ctas_per_sm = value; return KTB_OK;
     case 1: g_tma_ctas_per_sm = value; return KTB_OK;
     case 2: g_tma_cfg = value; return KTB_OK;
+    case 4: g_vec_flavor = value; return KTB_OK;
+    case 5: g_vec_unroll = value; return KTB_OK;
     case 3:
       KTB_REQUIRE(value >= KTB_VARIANT_VEC && value <= KTB_VARIANT_SCALAR, KTB_ERR_ARG,
                   "ktb_set_tuning: bad auto variant %d", value);

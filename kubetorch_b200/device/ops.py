@@ -189,6 +189,55 @@ def pack(
     return arena, offsets
 
 
+class PackPlan:
+    """A pack (or unpack) of a fixed set of tensors into a fixed arena with the ctypes descriptor
+    arrays built once: `run()` is one C call (no per-tensor Python work), graph-capturable."""
+
+    def __init__(self, tensors: Sequence[torch.Tensor], arena: Optional[torch.Tensor] = None):
+        self.dev = _check_dev_tensor(tensors[0], "tensors[0]")
+        ensure_init({self.dev})
+        self.tensors = list(tensors)
+        self.nbytes = [t.numel() * t.element_size() for t in tensors]
+        self.offsets, self.total = pack_layout(self.nbytes)
+        self.arena = arena if arena is not None else torch.empty(max(self.total, 1), dtype=torch.uint8,
+                                                                   device=f"cuda:{self.dev}")
+        n = len(tensors)
+        self._n = n
+        self._ptrs = L.arr(ctypes.c_void_p, [t.data_ptr() for t in tensors])
+        self._nb = L.arr(ctypes.c_size_t, self.nbytes)
+        self._offs = L.arr(ctypes.c_size_t, self.offsets)
+        self._arena_bytes = self.arena.numel() * self.arena.element_size()
+
+    def run(self, stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        L.call("ktb_pack", self.dev, self._ptrs, self._nb, self._n, self.arena.data_ptr(), self._arena_bytes,
+               self._offs, 0, _stream(self.dev, stream))
+        return self.arena
+
+    def run_unpack(self, stream: Optional[torch.cuda.Stream] = None):
+        L.call("ktb_unpack", self.dev, self.arena.data_ptr(), self._offs, self._nb, self._n, self._ptrs,
+               _stream(self.dev, stream))
+        return self.tensors
+
+
+class BatchPlan:
+    """n independent small calls out_i = op(x_i) with prebuilt descriptor arrays."""
+
+    def __init__(self, xs: Sequence[torch.Tensor], outs: Sequence[torch.Tensor], op: str, alpha=1.0, beta=0.0):
+        self.dev = _check_dev_tensor(xs[0], "xs[0]")
+        ensure_init({self.dev})
+        self.xs, self.outs = list(xs), list(outs)
+        self._src = L.arr(ctypes.c_void_p, [t.data_ptr() for t in xs])
+        self._dst = L.arr(ctypes.c_void_p, [t.data_ptr() for t in outs])
+        self._n_elems = L.arr(ctypes.c_size_t, [t.numel() for t in xs])
+        self._args = (OPS[op], dtype_code(xs[0].dtype), float(alpha), float(beta))
+
+    def run(self, stream: Optional[torch.cuda.Stream] = None):
+        op, dt, a, b = self._args
+        L.call("ktb_map_batch", self.dev, op, dt, self._src, self._dst, self._n_elems, len(self.xs), a, b,
+               _stream(self.dev, stream))
+        return self.outs
+
+
 def unpack(
     arena: torch.Tensor,
     offsets: Sequence[int],

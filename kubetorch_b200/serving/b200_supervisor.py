@@ -60,9 +60,10 @@ class B200Supervisor:
             if n in (None, "auto"):
                 n = torch.cuda.device_count()
             self.devices = list(range(int(n)))
-        if len(self.devices) > torch.cuda.device_count():
+        if self.devices and max(self.devices) >= torch.cuda.device_count():
             raise RuntimeError(
-                f"kt.Compute asked for {len(self.devices)} GPUs but only {torch.cuda.device_count()} are visible"
+                f"kt.Compute asked for GPU index {max(self.devices)} ({len(self.devices)} ranks) but only "
+                f"{torch.cuda.device_count()} GPUs are visible"
             )
         ops.ensure_init(self.devices)
         self._callable = instantiate(self.callable_obj, self.init_args) if self.callable_obj is not None \

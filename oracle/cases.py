@@ -106,3 +106,31 @@ def mlp_policy(obs, w1, w2, w3):
     h = torch.relu(o @ w1.t())
     h = torch.relu(h @ w2.t())
     return h @ w3.t()
+
+
+def torch_ddp(epochs):
+    """DDP smoke callable with the shape of the reference asset (tests/assets/torch_ddp/torch_ddp.py):
+    gloo process group from the env contract, a tiny DDP-wrapped Linear, `epochs` SGD steps."""
+    import torch
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    if not torch.distributed.is_initialized():
+        torch.distributed.init_process_group(backend="gloo")
+    model = DDP(torch.nn.Linear(10, 1))
+    opt = torch.optim.SGD(model.parameters(), lr=0.01)
+    for _ in range(epochs):
+        opt.zero_grad()
+        model(torch.randn(10)).sum().backward()
+        opt.step()
+    return "Success"
+
+
+def all_reduce_rank():
+    """Sum of ranks through a gloo all_reduce (tests/test_distributed.py:259-260 expects 6.0 at world 4)."""
+    import torch
+
+    if not torch.distributed.is_initialized():
+        torch.distributed.init_process_group(backend="gloo")
+    t = torch.tensor([float(os.environ["RANK"])])
+    torch.distributed.all_reduce(t)
+    return float(t.item())

@@ -49,11 +49,11 @@ DEFAULT_ALLOWED_SERIALIZATION = "json,pickle"
 DEFAULT_MASTER_PORT = 12345  # kt/serving/spmd/pytorch_process.py:21
 
 
-class HTTPError(Exception):
-    """Stand-in for fastapi.HTTPException(status_code, detail)."""
+class HTTPException(Exception):
+    """Stand-in for fastapi.HTTPException(status_code, detail); str(e) == "<status>: <detail>"."""
 
     def __init__(self, status_code: int, detail: str):
-        super().__init__(detail)
+        super().__init__(f"{status_code}: {detail}")
         self.status_code = status_code
         self.detail = detail
 
@@ -100,7 +100,7 @@ def deserialize_response(response_json: Any, serialization: str) -> Any:
 def parse_callable_params(params: Optional[dict], serialization: str, allowed: Optional[str] = None):
     allowed_list = (allowed if allowed is not None else os.getenv("KT_ALLOWED_SERIALIZATION", DEFAULT_ALLOWED_SERIALIZATION)).split(",")
     if serialization not in allowed_list:
-        raise HTTPError(400, f"Serialization format '{serialization}' not allowed. Allowed formats: {allowed_list}")
+        raise HTTPException(400, f"Serialization format '{serialization}' not allowed. Allowed formats: {allowed_list}")
     args, kwargs = [], {}
     if params:
         if serialization == "pickle":

@@ -1,0 +1,148 @@
+"""-m gpu: the public API (kt.fn / .to / remote __call__) on the B200 device backend against the
+recorded reference runtime results and the oracle."""
+import os
+
+import pytest
+import torch
+
+from conftest import resolve_args
+
+pytestmark = pytest.mark.gpu
+
+import kubetorch_b200 as kt  # noqa: E402
+from oracle import cases, ref_dispatch  # noqa: E402
+
+
+def _mapped(fn, *a, **k):
+    return kt.mapped(*a, **k)(fn)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    assert torch.cuda.is_available()
+
+
+def _deploy(fn, n_ranks, name):
+    comp = kt.Compute(gpus=1, allowed_serialization=["json", "pickle"]).distribute(
+        "b200", workers=1, num_proc=n_ranks, devices=[0] * n_ranks)
+    return kt.fn(fn, name=name).to(comp)
+
+
+def test_recorded_reference_calls_through_public_api(golden):
+    specs = {
+        "double": _mapped(cases.double, "scale", alpha=2.0),
+        "identity": _mapped(cases.identity, "identity"),
+        "scale": _mapped(cases.scale, "scale", alpha="alpha"),
+        "affine": _mapped(cases.affine, "affine", alpha="alpha", beta="beta"),
+    }
+    n = 0
+    for name, rec in golden["cases"].items():
+        if rec["status_code"] != 200 or rec["callable"] not in specs:
+            continue
+        args = resolve_args(golden, rec["args"])
+        remote = _deploy(specs[rec["callable"]], rec["distributed_config"]["num_proc"], f"t-{name}")
+        try:
+            for resident in ("device", "host"):
+                call_args = [a.cuda() if (resident == "device" and isinstance(a, torch.Tensor)) else a for a in args]
+                got = remote(*call_args, serialization="pickle")
+                assert isinstance(got, list) and len(got) == len(rec["result"])
+                for g, w in zip(got, rec["result"]):
+                    assert g.dtype == w.dtype and tuple(g.shape) == tuple(w.shape), (name, resident)
+                    assert torch.equal(g.cpu().view(torch.uint8), w.view(torch.uint8)), (name, resident)
+        finally:
+            remote.teardown()
+        n += 1
+    assert n >= 10
+
+
+def test_gather_reduce_through_public_api(golden):
+    ssum = _mapped(cases.shard_sum, "affine", alpha="alpha", beta="beta", reduce="sum")
+    remote = _deploy(ssum, 4, "t-sum")
+    try:
+        for name in ("sum_i64_130_x4", "sum_i32_515_x4"):
+            rec = golden["cases"][name]
+            args = resolve_args(golden, rec["args"])
+            got = remote(*[a.cuda() if isinstance(a, torch.Tensor) else a for a in args], serialization="pickle")
+            assert got == rec["result"], name
+        rec = golden["cases"]["sum_f32_1001_x4"]
+        x = resolve_args(golden, rec["args"])[0]
+        got = remote(x.cuda(), serialization="pickle")
+        tol = 8 * torch.finfo(torch.float32).eps * float(x.abs().sum())  # fp32 sum, order differs from torch
+        assert all(abs(g - w) <= tol for g, w in zip(got, rec["result"]))
+    finally:
+        remote.teardown()
+
+
+def test_non_distributed_gpu_call_returns_bare_tensor():
+    double = _mapped(cases.double, "scale", alpha=2.0)
+    remote = kt.fn(double, name="t-bare").to(kt.Compute(gpus=1))
+    try:
+        x = torch.randn(4099)
+        y = remote(x.cuda(), serialization="pickle")
+        assert isinstance(y, torch.Tensor) and torch.equal(y.cpu(), x * 2)
+    finally:
+        remote.teardown()
+
+
+def test_rows_are_the_shard_unit():
+    """2-D args shard like x.chunk(world) along dim 0 (whole rows), as the reference's user code does."""
+    double = _mapped(cases.double, "scale", alpha=2.0)
+    remote = _deploy(double, 4, "t-rows")
+    try:
+        x = torch.randn(10, 37)
+        want = ref_dispatch.spmd_call(cases.double, x, num_proc=4, serialization="pickle")
+        got = remote(x.cuda(), serialization="pickle")
+        assert [tuple(g.shape) for g in got] == [tuple(w.shape) for w in want]
+        assert all(torch.equal(g.cpu(), w) for g, w in zip(got, want))
+    finally:
+        remote.teardown()
+
+
+def test_errors_keep_the_reference_envelope():
+    double = _mapped(cases.double, "scale", alpha=2.0)
+    remote = kt.fn(double, name="t-err").to(
+        kt.Compute(gpus=1, allowed_serialization=["json"]).distribute("b200", num_proc=2, devices=[0, 0]))
+    try:
+        with pytest.raises(Exception) as ei:
+            remote(torch.ones(4).cuda(), serialization="pickle")
+        assert "Serialization format 'pickle' not allowed. Allowed formats: ['json']" in str(ei.value)
+        assert ei.value.pod_name and "Traceback" in ei.value.remote_traceback
+    finally:
+        remote.teardown()
+    r2 = _deploy(double, 2, "t-err2")
+    try:
+        with pytest.raises(TypeError) as ei:
+            r2("not a tensor", serialization="pickle")
+        assert ei.value.status_code == 422 if hasattr(ei.value, "status_code") else True
+    finally:
+        r2.teardown()
+
+
+def test_unmapped_callable_is_rejected_loudly():
+    remote = kt.fn(cases.summer, name="t-unmapped").to(kt.Compute(gpus=1).distribute("b200", num_proc=1))
+    try:
+        with pytest.raises(TypeError, match="not a @kt.mapped callable"):
+            remote(1, 2)
+    finally:
+        remote.teardown()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_peer_path_matches_oracle():
+    from kubetorch_b200.device import ops
+
+    ops.ensure_init([0, 1])
+    x = torch.randn((1 << 22) + 5)
+    want = torch.cat(ref_dispatch.spmd_call(cases.affine, x, 0.5, 1.5, num_proc=2, serialization="pickle"))
+    for variant in (1, 2):
+        y = ops.scatter_map_gather(x.cuda(0), "affine", 0.5, 1.5, devices=[0, 1], variant=variant)
+        torch.cuda.synchronize(0)
+        assert torch.equal(y.cpu(), want), variant
+    xi = torch.randint(-(2**40), 2**40, (100_003,), dtype=torch.int64)
+    total, partials = ops.scatter_map_reduce(xi.cuda(0), "identity", devices=[0, 1])
+    assert partials.tolist() == ref_dispatch.spmd_call(cases.shard_sum, xi, num_proc=2, serialization="pickle")
+    dst = torch.empty(1 << 20, dtype=torch.uint8, device="cuda:1")
+    src = torch.randint(0, 255, (1 << 20,), dtype=torch.uint8, device="cuda:0")
+    ops.broadcast(src, [dst])
+    torch.cuda.synchronize(0)
+    assert torch.equal(dst.cpu(), src.cpu())

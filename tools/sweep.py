@@ -51,11 +51,18 @@ def main():
     emit(what="torch_mul_256MiB", ms=ms, gbps=2 * nbytes / ms / 1e6)
 
     for op in ("scale", "identity"):
-        for cps in (2, 4, 6, 8, 16):
-            ops.set_tuning(0, cps)
-            ms = timeit(lambda: ops.map_tensor(x, op, 2.0, out=y, variant=L.VARIANT_VEC))
-            emit(what="map_vec", op=op, ctas_per_sm=cps, ms=ms, gbps=2 * nbytes / ms / 1e6)
-        ops.set_tuning(0, 4)
+        for un in (2, 4, 8):
+            for fl in (0, 1, 2, 3):
+                for cps in (0, 4, 6, 8, 12, 16, 32):
+                    ops.set_tuning(0, cps)
+                    ops.set_tuning(4, fl)
+                    ops.set_tuning(5, un)
+                    ms = timeit(lambda: ops.map_tensor(x, op, 2.0, out=y, variant=L.VARIANT_VEC))
+                    emit(what="map_vec", op=op, unroll=un, flavor=fl, ctas_per_sm=cps, ms=ms,
+                         gbps=2 * nbytes / ms / 1e6)
+        ops.set_tuning(0, 8)
+        ops.set_tuning(4, 0)
+        ops.set_tuning(5, 4)
         for cfg, per_sm_opts in ((0, (1,)), (1, (1,)), (2, (1, 2)), (3, (1,))):
             for per_sm in per_sm_opts:
                 ops.set_tuning(2, cfg)
@@ -93,9 +100,12 @@ def main():
     # pack: 1024 tensors of 256 KiB, and 4096 of 4 KiB
     for cnt, sz in ((1024, 1 << 18), (4096, 1 << 12), (8, 1 << 25)):
         ts = [torch.empty(sz, dtype=torch.uint8, device="cuda") for _ in range(cnt)]
-        arena, offs = ops.pack(ts)
-        ms = timeit(lambda: ops.pack(ts, arena=arena), iters=10)
-        emit(what="pack", count=cnt, seg_bytes=sz, ms=ms, gbps=2 * cnt * sz / ms / 1e6)
+        plan = ops.PackPlan(ts)
+        arena = plan.arena
+        ms = timeit(lambda: plan.run(), iters=10)
+        emit(what="pack_plan", count=cnt, seg_bytes=sz, ms=ms, gbps=2 * cnt * sz / ms / 1e6)
+        ms = timeit(lambda: ops.pack(ts, arena=arena), iters=5)
+        emit(what="pack_python_descs", count=cnt, seg_bytes=sz, ms=ms, gbps=2 * cnt * sz / ms / 1e6)
         cat_ms = timeit(lambda: torch.cat(ts), iters=10)
         emit(what="torch_cat", count=cnt, seg_bytes=sz, ms=cat_ms, gbps=2 * cnt * sz / cat_ms / 1e6)
         del ts, arena
@@ -103,8 +113,9 @@ def main():
     # batched small calls
     xs = [torch.randn(256, device="cuda") for _ in range(4096)]
     outs = [torch.empty_like(t) for t in xs]
-    ms = timeit(lambda: ops.map_batch(xs, "scale", 2.0, outs=outs), iters=10)
-    emit(what="map_batch_4096x1KiB", ms=ms, calls_per_sec=4096 / ms * 1e3)
+    bplan = ops.BatchPlan(xs, outs, "scale", 2.0)
+    ms = timeit(lambda: bplan.run(), iters=10)
+    emit(what="map_batch_plan_4096x1KiB", ms=ms, calls_per_sec=4096 / ms * 1e3)
     # same calls, one launch each, captured in a CUDA graph
     g = torch.cuda.CUDAGraph()
     s = torch.cuda.Stream()
@@ -128,7 +139,9 @@ def main():
     # host paths
     xh = torch.randn(n).pin_memory()
     yh = torch.empty_like(xh).pin_memory()
-    for chunk in (2 << 20, 8 << 20, 32 << 20):
+    ops.map_host(xh, "scale", 2.0, out_host=yh, chunk_bytes=8 << 20)  # warm-up (stage buffers, first touch)
+    for chunk in (2 << 20, 4 << 20, 8 << 20, 16 << 20):
+        ops.map_host(xh, "scale", 2.0, out_host=yh, chunk_bytes=chunk)
         t0 = time.perf_counter()
         for _ in range(3):
             ops.map_host(xh, "scale", 2.0, out_host=yh, chunk_bytes=chunk)
