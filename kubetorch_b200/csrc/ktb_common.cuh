@@ -208,6 +208,19 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t (&w)[8]) {
                "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
                : "memory");
 }
+// read-once / write-once streaming forms: no L1 allocation, first-to-evict in L2
+__device__ __forceinline__ void ldg256_stream(const void* p, uint32_t (&w)[8]) {
+  asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]),
+                 "=r"(w[7])
+               : "l"(p)
+               : "memory");
+}
+__device__ __forceinline__ void stg256_stream(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.L1::no_allocate.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
+               "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
 __device__ __forceinline__ void ldg128(const void* p, uint32_t (&w)[4]) {
   asm volatile("ld.global.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])

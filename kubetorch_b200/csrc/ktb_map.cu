@@ -19,16 +19,19 @@
 
 namespace ktb {
 
+extern int g_red_ctas_per_sm;  // ktb_reduce.cu
+
 // ---- tunables (ktb_set_tuning) ---------------------------------------------------------------
-static std::atomic<int> g_vec_ctas_per_sm{4};
+static std::atomic<int> g_vec_ctas_per_sm{0};  // 0 = one tile per CTA (measured best, profiles/r1_sweep.md)
 static std::atomic<int> g_tma_ctas_per_sm{1};
 static std::atomic<int> g_tma_cfg{0};       // 0: 4 x 32 KiB stages, 1: 6 x 32 KiB, 2: 8 x 16 KiB (2 CTA/SM)
 static std::atomic<int> g_auto_variant{KTB_VARIANT_VEC};
-static std::atomic<int> g_vec_flavor{0};    // cache flavor (experiments: F32-scale and identity only)
-static std::atomic<int> g_vec_unroll{4};    // 2 | 4 | 8 (experiments: same kernels)
+static std::atomic<int> g_vec_flavor{2};    // cache flavor (tunable for F32-scale and identity only)
+static std::atomic<int> g_vec_unroll{2};    // 2 | 4 | 8 (tunable for the same kernels)
 
 constexpr int kVecThreads = 256;
-constexpr int kVecUnroll = 4;
+constexpr int kVecUnroll = 2;   // defaults measured on B200: 2 x 256-bit loads in flight per thread,
+constexpr int kVecFlavor = 2;   // L2::evict_first streaming hints, one 16 KiB tile per CTA
 
 // ---- VEC -----------------------------------------------------------------------------------------
 // FL (cache flavor, 256-bit path only): 0 = L1::no_allocate, 1 = default caching,
@@ -77,7 +80,7 @@ __device__ __forceinline__ void st_vec(uint8_t* p, const uint32_t (&w)[VB / 4]) 
   }
 }
 
-template <int DT, int OP, int VB, int FL = 0, int UNROLL = kVecUnroll>
+template <int DT, int OP, int VB, int FL = kVecFlavor, int UNROLL = kVecUnroll>
 __global__ void __launch_bounds__(kVecThreads)
     map_vec_kernel(const uint8_t* src, uint8_t* dst, size_t n_bytes, MapParams p) {
   constexpr int NW = VB / 4;
@@ -238,8 +241,8 @@ static int launch_typed(int dev, const uint8_t* src, uint8_t* dst, size_t n_elem
     };
     if ((both & 31) == 0) {
       constexpr bool kTunable = (DT == KTB_U8) || (DT == KTB_F32 && OP == KTB_OP_SCALE);
-      const int fl = kTunable ? g_vec_flavor.load() : 0;
-      const int un = kTunable ? g_vec_unroll.load() : 4;
+      const int fl = kTunable ? g_vec_flavor.load() : kVecFlavor;
+      const int un = kTunable ? g_vec_unroll.load() : kVecUnroll;
 #define KTB_VEC32(FL, UN)                                                                          \
   map_vec_kernel<DT, OP, 32, FL, UN>                                                               \
       <<<grid_for((size_t)kVecThreads * (UN)*32), kVecThreads, 0, stream>>>(src, dst, n_bytes, p)
@@ -253,7 +256,7 @@ static int launch_typed(int dev, const uint8_t* src, uint8_t* dst, size_t n_elem
         }
       } else {
         (void)fl; (void)un;
-        KTB_VEC32(0, 4);
+        KTB_VEC32(kVecFlavor, kVecUnroll);
       }
 #undef KTB_VEC32
     } else {
@@ -351,6 +354,7 @@ int ktb_set_tuning(int key, int value) {
     case 2: g_tma_cfg = value; return KTB_OK;
     case 4: g_vec_flavor = value; return KTB_OK;
     case 5: g_vec_unroll = value; return KTB_OK;
+    case 6: g_red_ctas_per_sm = value > 0 ? value : 8; return KTB_OK;
     case 3:
       KTB_REQUIRE(value >= KTB_VARIANT_VEC && value <= KTB_VARIANT_SCALAR, KTB_ERR_ARG,
                   "ktb_set_tuning: bad auto variant %d", value);

@@ -47,10 +47,34 @@ __global__ void __launch_bounds__(kSegThreads) seg_map_kernel(const __grid_const
     const size_t len = (seg_bytes - off) < (size_t)kSegTile ? (seg_bytes - off) : (size_t)kSegTile;
     const uint8_t* s = b.src[lo] + off;
     uint8_t* d = b.dst[lo] + off;
-    if (((((uintptr_t)s) | ((uintptr_t)d)) & 15) == 0) {
+    const uintptr_t both = ((uintptr_t)s) | ((uintptr_t)d);
+    if ((both & 31) == 0) {
+      // 256-bit streaming path: a full tile is 1024 packets = 4 per thread, all loads issued first
+      const size_t nv = len >> 5;
+      size_t v = threadIdx.x;
+      for (; v + 3 * kSegThreads < nv; v += 4 * kSegThreads) {
+        uint32_t w[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ldg256_stream(s + ((v + j * kSegThreads) << 5), w[j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          apply_words<DT, OP, 8>(w[j], p);
+          stg256_stream(d + ((v + j * kSegThreads) << 5), w[j]);
+        }
+      }
+      for (; v < nv; v += kSegThreads) {
+        uint32_t w0[8];
+        ldg256_stream(s + (v << 5), w0);
+        apply_words<DT, OP, 8>(w0, p);
+        stg256_stream(d + (v << 5), w0);
+      }
+      const size_t tail = nv << 5;
+      for (size_t e = threadIdx.x; e < (len - tail) / ES; e += kSegThreads)
+        apply_elem<DT, OP>(s + tail + e * ES, d + tail + e * ES, p);
+    } else if ((both & 15) == 0) {
       const size_t nv = len >> 4;
       size_t v = threadIdx.x;
-      // two 16-byte loads in flight per thread per step (tile = 2048 vectors = 8 steps of 256)
+      // two 16-byte loads in flight per thread per step
       for (; v + kSegThreads < nv; v += 2 * kSegThreads) {
         uint32_t w0[4], w1[4];
         ldg128(s + (v << 4), w0);
@@ -81,7 +105,8 @@ static int launch_seg_typed(int dev, const SegBatch& b, const MapParams& p, cuda
   const DeviceInfo* di = device_info(dev);
   const uint32_t n_tiles = b.tile_prefix[b.n];
   if (n_tiles == 0) return KTB_OK;
-  int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)di->sm_count * 8);
+  (void)di;
+  int grid = (int)n_tiles;  // one 32 KiB tile per CTA: the hardware scheduler balances ragged segments
   seg_map_kernel<DT, OP><<<grid, kSegThreads, 0, stream>>>(b, p);
   KTB_CK(cudaGetLastError());
   return KTB_OK;

@@ -16,6 +16,7 @@ namespace ktb {
 constexpr int kRedThreads = 256;
 constexpr int kRedMaxGrid = 2048;
 constexpr size_t kRedHeader = 64;  // counter lives in the first 64 bytes of the workspace
+int g_red_ctas_per_sm = 8;         // ktb_set_tuning key 6
 
 template <int DT>
 struct Acc {
@@ -44,19 +45,18 @@ __device__ __forceinline__ typename Acc<DT>::type elem_value(const uint8_t* p, c
   }
 }
 
-// Sum of the op-mapped elements held in four 32-bit words.
-template <int DT, int OP>
-__device__ __forceinline__ typename Acc<DT>::type words_value(const uint32_t (&w)[4], const MapParams& mp) {
+// Sum of the op-mapped elements held in NW 32-bit words.
+template <int DT, int OP, int NW>
+__device__ __forceinline__ typename Acc<DT>::type words_value(const uint32_t (&w)[NW], const MapParams& mp) {
   if constexpr (DT == KTB_F32) {
-    float s = apply_f32<OP>(__uint_as_float(w[0]), mp);
-    s += apply_f32<OP>(__uint_as_float(w[1]), mp);
-    s += apply_f32<OP>(__uint_as_float(w[2]), mp);
-    s += apply_f32<OP>(__uint_as_float(w[3]), mp);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) s += apply_f32<OP>(__uint_as_float(w[i]), mp);
     return s;
   } else if constexpr (DT == KTB_BF16) {
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NW; ++i) {
       s += apply_bf16_as_f32<OP>(__uint_as_float(w[i] << 16), mp);
       s += apply_bf16_as_f32<OP>(__uint_as_float(w[i] & 0xffff0000u), mp);
     }
@@ -64,12 +64,14 @@ __device__ __forceinline__ typename Acc<DT>::type words_value(const uint32_t (&w
   } else if constexpr (DT == KTB_I32) {
     long long s = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) s += (long long)(int)apply_i32<OP>(w[i], mp);
+    for (int i = 0; i < NW; ++i) s += (long long)(int)apply_i32<OP>(w[i], mp);
     return s;
   } else {
-    unsigned long long a = ((unsigned long long)w[1] << 32) | w[0];
-    unsigned long long b = ((unsigned long long)w[3] << 32) | w[2];
-    return (long long)(apply_i64<OP>(a, mp) + apply_i64<OP>(b, mp));
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < NW; i += 2)
+      s += apply_i64<OP>(((unsigned long long)w[i + 1] << 32) | w[i], mp);
+    return (long long)s;
   }
 }
 
@@ -107,31 +109,31 @@ __global__ void __launch_bounds__(kRedThreads)
   __shared__ bool is_last;
 
   const size_t n_bytes = n_elems * ES;
-  const bool vec_ok = (((uintptr_t)src) & 15) == 0;
-  const size_t n_vec = vec_ok ? (n_bytes >> 4) : 0;
+  const bool vec_ok = (((uintptr_t)src) & 31) == 0;
+  const size_t n_vec = vec_ok ? (n_bytes >> 5) : 0;  // 32-byte packets
 
   A acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
   const size_t stride = (size_t)gridDim.x * kRedThreads;
   size_t v = (size_t)blockIdx.x * kRedThreads + threadIdx.x;
-  // 4 independent 16-byte loads in flight per thread
+  // 4 independent 256-bit loads in flight per thread
   for (; v + 3 * stride < n_vec; v += 4 * stride) {
-    uint32_t w0[4], w1[4], w2[4], w3[4];
-    ldg128(src + (v << 4), w0);
-    ldg128(src + ((v + stride) << 4), w1);
-    ldg128(src + ((v + 2 * stride) << 4), w2);
-    ldg128(src + ((v + 3 * stride) << 4), w3);
-    acc0 += words_value<DT, OP>(w0, mp);
-    acc1 += words_value<DT, OP>(w1, mp);
-    acc2 += words_value<DT, OP>(w2, mp);
-    acc3 += words_value<DT, OP>(w3, mp);
+    uint32_t w0[8], w1[8], w2[8], w3[8];
+    ldg256_stream(src + (v << 5), w0);
+    ldg256_stream(src + ((v + stride) << 5), w1);
+    ldg256_stream(src + ((v + 2 * stride) << 5), w2);
+    ldg256_stream(src + ((v + 3 * stride) << 5), w3);
+    acc0 += words_value<DT, OP, 8>(w0, mp);
+    acc1 += words_value<DT, OP, 8>(w1, mp);
+    acc2 += words_value<DT, OP, 8>(w2, mp);
+    acc3 += words_value<DT, OP, 8>(w3, mp);
   }
   for (; v < n_vec; v += stride) {
-    uint32_t w0[4];
-    ldg128(src + (v << 4), w0);
-    acc0 += words_value<DT, OP>(w0, mp);
+    uint32_t w0[8];
+    ldg256_stream(src + (v << 5), w0);
+    acc0 += words_value<DT, OP, 8>(w0, mp);
   }
-  // element tail (everything when the pointer is not 16-byte aligned)
-  const size_t tail0 = (n_vec << 4) / ES;
+  // element tail (everything when the pointer is not 32-byte aligned)
+  const size_t tail0 = (n_vec << 5) / ES;
   for (size_t e = tail0 + (size_t)blockIdx.x * kRedThreads + threadIdx.x; e < n_elems; e += stride)
     acc1 += elem_value<DT, OP>(src + e * ES, mp);
 
@@ -176,9 +178,9 @@ template <int DT, int OP>
 static int launch_reduce_typed(int dev, const uint8_t* src, size_t n_elems, const MapParams& p,
                                void* out, void* ws, cudaStream_t stream) {
   const DeviceInfo* di = device_info(dev);
-  size_t blocks = (n_elems + (size_t)kRedThreads * 16 - 1) / ((size_t)kRedThreads * 16);
+  size_t blocks = (n_elems + (size_t)kRedThreads * 32 - 1) / ((size_t)kRedThreads * 32);
   int grid = (int)std::min<size_t>(std::max<size_t>(blocks, 1),
-                                   std::min<size_t>((size_t)di->sm_count * 4, kRedMaxGrid));
+                                   std::min<size_t>((size_t)di->sm_count * g_red_ctas_per_sm, kRedMaxGrid));
   map_reduce_kernel<DT, OP><<<grid, kRedThreads, 0, stream>>>(src, n_elems, p, out, (uint8_t*)ws);
   KTB_CK(cudaGetLastError());
   return KTB_OK;

@@ -291,6 +291,12 @@ def _execute_rank(fn, params: dict, serialization: str, env: Dict[str, str], all
             return ("__error__",) + package_exception(e)
 
 
+def _with_status(exc, status: int):
+    """Oracle-only: remember the HTTP status the reference server would have answered with."""
+    exc.http_status = status
+    return exc
+
+
 def _wire(body: dict) -> dict:
     """The HTTP hop: the body is JSON-encoded by httpx and JSON-decoded by FastAPI."""
     return json.loads(json.dumps(body))
@@ -301,7 +307,7 @@ def local_call(fn, *args, serialization: str = "json", allowed: Optional[str] = 
     body = _wire(serialize_body(build_call_body(*args, **kwargs), serialization))
     res = _execute_rank(fn, body, serialization, {}, allowed)
     if isinstance(res, tuple) and res and res[0] == "__error__":
-        raise rehydrate_exception(res[2])
+        raise _with_status(rehydrate_exception(res[2]), res[1])
     return deserialize_response(_wire(res) if serialization != "none" else res, serialization)
 
 
@@ -320,7 +326,11 @@ def spmd_call(
     worker_ips = worker_ips or ["localhost"]
     body = _wire(serialize_body(build_call_body(*args, **kwargs), serialization))
     workers_arg = body.get("workers")
-    select_workers(workers_arg, worker_ips, worker_ips[0])  # raises the reference's selector errors
+    try:
+        select_workers(workers_arg, worker_ips, worker_ips[0])  # raises the reference's selector errors
+    except ValueError as e:
+        status, envelope = package_exception(e)
+        raise _with_status(rehydrate_exception(envelope), status)
     responses = []
     for local_rank in range(num_proc):
         # mp.Queue pickles the params dict once per rank: each rank decodes its own copy
@@ -328,7 +338,7 @@ def spmd_call(
         env = rank_env(distribution_type, worker_ips, 0, local_rank, num_proc, port)
         res = _execute_rank(fn, params, serialization, env, allowed)
         if isinstance(res, tuple) and res and res[0] == "__error__":
-            raise rehydrate_exception(res[2])  # fast-fail on the first failing rank
+            raise _with_status(rehydrate_exception(res[2]), res[1])  # fast-fail on the first failing rank
         responses.append(res)
     return deserialize_response(_wire(responses), serialization)
 

@@ -75,7 +75,7 @@ def test_oracle_matches_recorded_reference_runtime(golden):
             err = rec["error"]
             assert _base_name(ei.value) == err["error_type"], name
             assert ei.value.args[0].split("\n\n")[0] == err["message"], name
-            assert R.status_code_for(ei.value) == rec["status_code"], name
+            assert ei.value.http_status == rec["status_code"], name
         n += 1
     assert n >= 30
 
