@@ -118,7 +118,8 @@ int ktb_shard_bounds(size_t n, int world, int rank, size_t* begin, size_t* end);
  * pointers valid on `dev`; they must be element-aligned and must not partially overlap
  * (src == dst is allowed).  alpha/beta are converted to the dtype's op-math type
  * (float for F32/BF16, int64 for I32/I64).  KTB_U8 supports KTB_OP_IDENTITY only.
- * KTB_VARIANT_TMA requires 16-byte aligned src and dst. */
+ * KTB_VARIANT_TMA / _VEC need 16-byte aligned src and dst and silently use the next narrower
+ * path otherwise (all variants are bit-identical). */
 int ktb_map(int dev, int op, int dtype, const void* src, void* dst, size_t n_elems,
             double alpha, double beta, int variant, uintptr_t stream);
 

@@ -154,7 +154,9 @@ int ktb_scatter_map_gather(int op, int dtype, const void* src_root, void* dst_ro
     const int dev = devs[r];
     KTB_GUARD(dev);
     cudaStream_t st = stream_of(r);
-    const bool is_root = (r == root_rank) || (st == root_stream);
+    // same ordering domain as the root only if it is the same stream ON the same device (handle 0 is
+    // "the default stream of whichever device is current", so handles alone do not identify a stream)
+    const bool is_root = (r == root_rank) || (dev == root_dev && st == root_stream);
     if (!is_root) KTB_CK(cudaStreamWaitEvent(st, root->ev_a, 0));
     rc = launch_map(dev, op, dtype, static_cast<const uint8_t*>(src_root) + b * es,
                     static_cast<uint8_t*>(dst_root) + b * es, e - b, p, variant, st);
@@ -201,7 +203,9 @@ int ktb_scatter_map_reduce(int op, int dtype, const void* src_root, size_t n_ele
     const int dev = devs[r];
     KTB_GUARD(dev);
     cudaStream_t st = stream_of(r);
-    const bool is_root = (r == root_rank) || (st == root_stream);
+    // same ordering domain as the root only if it is the same stream ON the same device (handle 0 is
+    // "the default stream of whichever device is current", so handles alone do not identify a stream)
+    const bool is_root = (r == root_rank) || (dev == root_dev && st == root_stream);
     if (!is_root) KTB_CK(cudaStreamWaitEvent(st, root->ev_a, 0));
     KTB_REQUIRE(workspaces[r], KTB_ERR_ARG, "ktb_scatter_map_reduce: workspaces[%d] is null", r);
     // empty shards still write a zero partial (n_elems = 0 → kernel stores 0)

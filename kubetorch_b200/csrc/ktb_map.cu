@@ -224,10 +224,8 @@ static int launch_typed(int dev, const uint8_t* src, uint8_t* dst, size_t n_elem
   const uintptr_t both = (uintptr_t)src | (uintptr_t)dst;
 
   if (variant == KTB_VARIANT_AUTO) variant = g_auto_variant.load();
-  if (variant == KTB_VARIANT_TMA && (both & 15)) {
-    set_error("ktb_map: KTB_VARIANT_TMA needs 16-byte aligned src/dst (got %p, %p)", src, dst);
-    return KTB_ERR_ARG;
-  }
+  // bulk (TMA) and vector paths need 16-byte aligned pointers; ragged shard boundaries fall back
+  if (variant == KTB_VARIANT_TMA && (both & 15)) variant = KTB_VARIANT_VEC;
   if (variant == KTB_VARIANT_VEC && (both & 15)) variant = KTB_VARIANT_SCALAR;
 
   if (variant == KTB_VARIANT_VEC) {
