@@ -186,6 +186,32 @@ int ktb_scatter_map_reduce(int op, int dtype, const void* src_root, size_t n_ele
                            void* partials_root, void* out_root, void* const* workspaces,
                            const uintptr_t* streams);
 
+/* ---- push/push pipeline: in-kernel flag synchronisation, no host sync on the data path ----------- */
+
+/* Bytes of a control block (zero-initialised device memory; one per rank, one for the root). */
+size_t ktb_push_control_bytes(void);
+/* ROOT side of call number `seq` (1,2,3,... — every participant counts calls identically): for each
+ * of n_chunks pieces, peer-store the piece of every non-root rank's shard into
+ * stage_peer[r] + (seq&1)*stage_stride and publish ready[chunk] = seq in ctrl_peer[r].  The kernel
+ * itself waits for ack[r] >= seq-2 (in ctrl_root) before overwriting a staging half.
+ * stage_peer[r] / ctrl_peer[r] are pointers valid on root_dev (peer access or CUDA IPC). */
+int ktb_push_scatter(int root_dev, const void* src_root, size_t n_elems, size_t granule, int dtype,
+                     int n_ranks, int root_rank, void* const* stage_peer, size_t stage_stride,
+                     void* const* ctrl_peer, void* ctrl_root, int n_chunks, unsigned long long seq,
+                     uintptr_t stream);
+/* RANK side: for each piece, spin in-kernel until ready[chunk] >= seq, then
+ * dst_root_shard[piece] = op(stage_local[piece]) (peer stores into the root's result arena); after the
+ * last piece publish ack[rank] = seq in the root's control block (ctrl_root_peer). */
+int ktb_push_consume(int dev, int op, int dtype, const void* stage_local, size_t stage_stride,
+                     void* dst_root_shard, size_t shard_elems, double alpha, double beta,
+                     void* ctrl_local, void* ctrl_root_peer, int rank, int n_chunks,
+                     unsigned long long seq, uintptr_t stream);
+/* ROOT: stream-ordered completion of call `seq` (spins until every ack[r] >= seq). */
+int ktb_push_wait(int root_dev, void* ctrl_root, int n_ranks, int root_rank, unsigned long long seq,
+                  uintptr_t stream);
+/* Synchronously read a control block's sticky status: 0 healthy, 1 = an in-kernel wait timed out. */
+int ktb_push_status(int dev, const void* ctrl, unsigned int* out);
+
 /* ---- host-resident args/results (the reference's client lives outside the GPU) -------------------- */
 
 /* dst_host = op(src_host) with both buffers in pinned host memory, chunked through

@@ -1,0 +1,335 @@
+// ktb_push.cu — the push/push form of scatter → exec → gather, synchronised INSIDE the kernels.
+//
+// ktb_scatter_map_gather (ktb_dispatch.cu) has every rank PULL its shard from the root (peer loads)
+// and PUSH its result back (peer stores): one kernel per rank, but the rank's NVLink port then carries
+// read requests + write data one way and read data + write acks the other, and measured only ~0.6 of
+// the link per direction (profiles/r1_peer_sweep.md).  Here both directions carry posted writes only:
+//
+//   root  : push_scatter_kernel  — for chunk c, peer-STORE chunk c of every rank's shard into that
+//           rank's staging buffer, then publish ready[r][c] = seq (st.release.sys) in the rank's memory
+//   rank r: push_consume_kernel  — spin (ld.acquire.sys, local memory) until ready[c] >= seq, apply the
+//           op to the staged chunk (local HBM read) and peer-STORE the result into the root's result
+//           arena; after the last chunk publish ack[r] = seq in the root's memory
+//   root  : push_wait_kernel     — stream-ordered completion: spin until every ack[r] >= seq
+//
+// The flags replace host-side events, so the same code serves one controller process driving N GPUs
+// and one process per GPU (CUDA IPC arenas): there is no host synchronisation on the data path at all.
+// Staging is double-buffered by call parity; the root does not overwrite buffer (seq & 1) before the
+// rank has acknowledged call seq-2.  Every spin carries a wall-clock timeout that raises a sticky
+// status word instead of hanging the GPU.
+//
+// Replaces: kt/serving/spmd/spmd_supervisor.py:366-570 (fan-out, wait loop, concat) and
+// kt/serving/remote_worker_pool.py:254-395 (per-pod POST + gather).
+#include "ktb_common.cuh"
+
+#include <algorithm>
+
+namespace ktb {
+
+constexpr int kPushMaxRanks = 16;
+constexpr int kPushThreads = 256;
+constexpr uint32_t kPushTile = 16384;          // bytes per CTA
+constexpr unsigned long long kSpinTimeoutNs = 10ull * 1000 * 1000 * 1000;  // 10 s
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Spin until *flag >= want. Returns false on timeout (and records it in *status).
+__device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long want,
+                                           unsigned int* status) {
+  if (ld_acquire_sys(flag) >= want) return true;
+  const unsigned long long t0 = globaltimer_ns();
+  while (ld_acquire_sys(flag) < want) {
+    __nanosleep(200);
+    if (globaltimer_ns() - t0 > kSpinTimeoutNs) {
+      atomicExch(status, 1u);
+      return false;
+    }
+  }
+  return true;
+}
+
+struct PushScatterArgs {
+  const uint8_t* src[kPushMaxRanks];             // root-local source of this chunk, per destination
+  uint8_t* dst[kPushMaxRanks];                   // peer staging destination
+  unsigned long long nbytes[kPushMaxRanks];
+  uint32_t tile_prefix[kPushMaxRanks + 1];
+  unsigned long long* ready[kPushMaxRanks];      // peer: &ready_r[chunk]
+  const unsigned long long* ack[kPushMaxRanks];  // root-local: &ack[r]
+  int n;
+  unsigned long long seq;
+};
+
+__global__ void __launch_bounds__(kPushThreads)
+    push_scatter_kernel(const __grid_constant__ PushScatterArgs a, unsigned int* ticket, unsigned int* status) {
+  const uint32_t t = blockIdx.x;
+  int seg = 0;
+  while (seg + 1 < a.n && a.tile_prefix[seg + 1] <= t) ++seg;
+  // do not overwrite staging buffer (seq & 1) before the rank consumed call seq-2
+  if (a.seq > 2) {
+    __shared__ bool ok;
+    if (threadIdx.x == 0) ok = spin_until(a.ack[seg], a.seq - 2, status);
+    __syncthreads();
+    (void)ok;
+  }
+  const size_t off = (size_t)(t - a.tile_prefix[seg]) * kPushTile;
+  const size_t seg_bytes = (size_t)a.nbytes[seg];
+  const size_t len = (seg_bytes - off) < (size_t)kPushTile ? (seg_bytes - off) : (size_t)kPushTile;
+  const uint8_t* s = a.src[seg] + off;
+  uint8_t* d = a.dst[seg] + off;
+  if (((((uintptr_t)s) | ((uintptr_t)d)) & 31) == 0) {
+    const size_t nv = len >> 5;   // a full tile = 512 packets = 2 per thread, both loads first
+    uint32_t w0[8], w1[8];
+    const size_t v0 = threadIdx.x, v1 = threadIdx.x + kPushThreads;
+    if (v0 < nv) ldg256_stream(s + (v0 << 5), w0);
+    if (v1 < nv) ldg256_stream(s + (v1 << 5), w1);
+    if (v0 < nv) stg256(d + (v0 << 5), w0);
+    if (v1 < nv) stg256(d + (v1 << 5), w1);
+    for (size_t e = (nv << 5) + threadIdx.x; e < len; e += kPushThreads) d[e] = s[e];
+  } else {
+    for (size_t e = threadIdx.x; e < len; e += kPushThreads) d[e] = s[e];
+  }
+  // last CTA of the launch publishes "chunk landed" to every rank
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    if (threadIdx.x < a.n) {
+      __threadfence_system();
+      st_release_sys(a.ready[threadIdx.x], a.seq);
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+  }
+}
+
+// Publish-only launch for empty chunks (keeps the flag protocol uniform).
+__global__ void push_publish_kernel(const __grid_constant__ PushScatterArgs a) {
+  if (threadIdx.x < a.n) st_release_sys(a.ready[threadIdx.x], a.seq);
+}
+
+template <int DT, int OP>
+__global__ void __launch_bounds__(kPushThreads)
+    push_consume_kernel(const uint8_t* stage, uint8_t* dst, size_t n_bytes, MapParams p,
+                        const unsigned long long* ready, unsigned long long seq, unsigned long long* ack,
+                        int publish_ack, unsigned int* ticket, unsigned int* status) {
+  constexpr size_t ES = (DT == KTB_U8) ? 1 : (DT == KTB_BF16 ? 2 : (DT == KTB_I64 ? 8 : 4));
+  __shared__ bool flag;
+  if (threadIdx.x == 0) flag = spin_until(ready, seq, status);
+  __syncthreads();
+  const size_t off = (size_t)blockIdx.x * kPushTile;
+  if (off < n_bytes) {
+    const size_t len = (n_bytes - off) < (size_t)kPushTile ? (n_bytes - off) : (size_t)kPushTile;
+    const uint8_t* s = stage + off;
+    uint8_t* d = dst + off;
+    if (((((uintptr_t)s) | ((uintptr_t)d)) & 31) == 0) {
+      const size_t nv = len >> 5;
+      uint32_t w0[8], w1[8];
+      const size_t v0 = threadIdx.x, v1 = threadIdx.x + kPushThreads;
+      if (v0 < nv) ldg256_stream(s + (v0 << 5), w0);
+      if (v1 < nv) ldg256_stream(s + (v1 << 5), w1);
+      if (v0 < nv) {
+        apply_words<DT, OP, 8>(w0, p);
+        stg256(d + (v0 << 5), w0);
+      }
+      if (v1 < nv) {
+        apply_words<DT, OP, 8>(w1, p);
+        stg256(d + (v1 << 5), w1);
+      }
+      const size_t tail = nv << 5;
+      for (size_t e = threadIdx.x; e < (len - tail) / ES; e += kPushThreads)
+        apply_elem<DT, OP>(s + tail + e * ES, d + tail + e * ES, p);
+    } else {
+      for (size_t e = threadIdx.x; e < len / ES; e += kPushThreads) apply_elem<DT, OP>(s + e * ES, d + e * ES, p);
+    }
+  }
+  if (publish_ack) {
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+      __threadfence_system();
+      st_release_sys(ack, seq);   // results of the whole shard are in the root's memory
+      *ticket = 0;
+    }
+  }
+}
+
+__global__ void push_wait_kernel(const unsigned long long* ack, int n_ranks, int root_rank, unsigned long long seq,
+                                 unsigned int* status) {
+  const int r = threadIdx.x;
+  if (r < n_ranks && r != root_rank) spin_until(&ack[r], seq, status);
+}
+
+// Chunk c of a shard of `shard_elems` elements: element range [b, e), chunk size rounded to 64 elements.
+static inline void chunk_bounds(size_t shard_elems, int n_chunks, int c, size_t* b, size_t* e) {
+  size_t per = (shard_elems + (size_t)n_chunks - 1) / (size_t)n_chunks;
+  per = (per + 63) / 64 * 64;
+  size_t lo = std::min(shard_elems, per * (size_t)c);
+  size_t hi = std::min(shard_elems, lo + per);
+  *b = lo;
+  *e = hi;
+}
+
+}  // namespace ktb
+
+using namespace ktb;
+
+extern "C" {
+
+size_t ktb_push_control_bytes(void) { return 4096; }
+
+// Layout of a control block (zero-initialised, one per device, ktb_push_control_bytes() long):
+//   [   0,  512)  ready[c]  (u64 per chunk, written by the root into the RANK's block)
+//   [ 512, 1024)  ack[r]    (u64 per rank, written by rank r into the ROOT's block)
+//   [1024, 1028)  ticket    (u32, local)
+//   [1032, 1036)  status    (u32, local; nonzero = a spin timed out)
+#define KTB_CTRL_READY 0
+#define KTB_CTRL_ACK 512
+#define KTB_CTRL_TICKET 1024
+#define KTB_CTRL_STATUS 1032
+#define KTB_PUSH_MAX_CHUNKS 64
+
+int ktb_push_scatter(int root_dev, const void* src_root, size_t n_elems, size_t granule, int dtype, int n_ranks,
+                     int root_rank, void* const* stage_peer, size_t stage_stride, void* const* ctrl_peer,
+                     void* ctrl_root, int n_chunks, unsigned long long seq, uintptr_t stream) {
+  int rc = require_device(root_dev);
+  if (rc) return rc;
+  const size_t es = dtype_size(dtype);
+  KTB_REQUIRE(es != 0, KTB_ERR_ARG, "ktb_push_scatter: unknown dtype %d", dtype);
+  KTB_REQUIRE(n_ranks > 0 && n_ranks <= kPushMaxRanks && root_rank >= 0 && root_rank < n_ranks, KTB_ERR_ARG,
+              "ktb_push_scatter: bad ranks %d/%d", root_rank, n_ranks);
+  KTB_REQUIRE(n_chunks > 0 && n_chunks <= KTB_PUSH_MAX_CHUNKS, KTB_ERR_ARG, "ktb_push_scatter: n_chunks %d out of range",
+              n_chunks);
+  KTB_REQUIRE(src_root && stage_peer && ctrl_peer && ctrl_root && seq > 0, KTB_ERR_ARG, "ktb_push_scatter: null argument");
+  KTB_REQUIRE(granule > 0 && n_elems % granule == 0, KTB_ERR_ARG, "ktb_push_scatter: n_elems not a multiple of granule");
+  KTB_GUARD(root_dev);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* croot = static_cast<uint8_t*>(ctrl_root);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(croot + KTB_CTRL_TICKET);
+  unsigned int* status = reinterpret_cast<unsigned int*>(croot + KTB_CTRL_STATUS);
+  const size_t buf_off = (size_t)(seq & 1) * stage_stride;
+  for (int c = 0; c < n_chunks; ++c) {
+    PushScatterArgs a;
+    a.n = 0;
+    a.seq = seq;
+    a.tile_prefix[0] = 0;
+    for (int r = 0; r < n_ranks; ++r) {
+      if (r == root_rank) continue;
+      size_t sb = 0, se = 0, cb = 0, ce = 0;
+      ktb_shard_bounds(n_elems / granule, n_ranks, r, &sb, &se);
+      sb *= granule;
+      se *= granule;
+      chunk_bounds(se - sb, n_chunks, c, &cb, &ce);
+      KTB_REQUIRE(stage_peer[r] && ctrl_peer[r], KTB_ERR_ARG, "ktb_push_scatter: rank %d has no staging/control block", r);
+      KTB_REQUIRE((se - sb) * es <= stage_stride, KTB_ERR_ARG, "ktb_push_scatter: shard of rank %d exceeds stage_stride", r);
+      const int i = a.n++;
+      a.src[i] = static_cast<const uint8_t*>(src_root) + (sb + cb) * es;
+      a.dst[i] = static_cast<uint8_t*>(stage_peer[r]) + buf_off + cb * es;
+      a.nbytes[i] = (ce - cb) * es;
+      a.tile_prefix[i + 1] = a.tile_prefix[i] + (uint32_t)(((ce - cb) * es + kPushTile - 1) / kPushTile);
+      a.ready[i] = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ctrl_peer[r]) + KTB_CTRL_READY) + c;
+      a.ack[i] = reinterpret_cast<const unsigned long long*>(croot + KTB_CTRL_ACK) + r;
+    }
+    if (a.n == 0) continue;
+    const uint32_t tiles = a.tile_prefix[a.n];
+    if (tiles == 0)
+      push_publish_kernel<<<1, 32, 0, st>>>(a);
+    else
+      push_scatter_kernel<<<tiles, kPushThreads, 0, st>>>(a, ticket, status);
+    KTB_CK(cudaGetLastError());
+  }
+  return KTB_OK;
+}
+
+int ktb_push_consume(int dev, int op, int dtype, const void* stage_local, size_t stage_stride, void* dst_root_shard,
+                     size_t shard_elems, double alpha, double beta, void* ctrl_local, void* ctrl_root_peer, int rank,
+                     int n_chunks, unsigned long long seq, uintptr_t stream) {
+  int rc = require_device(dev);
+  if (rc) return rc;
+  const size_t es = dtype_size(dtype);
+  KTB_REQUIRE(es != 0, KTB_ERR_ARG, "ktb_push_consume: unknown dtype %d", dtype);
+  KTB_REQUIRE(op >= KTB_OP_IDENTITY && op <= KTB_OP_AFFINE && !(dtype == KTB_U8 && op != KTB_OP_IDENTITY), KTB_ERR_ARG,
+              "ktb_push_consume: bad op/dtype %d/%d", op, dtype);
+  KTB_REQUIRE(n_chunks > 0 && n_chunks <= KTB_PUSH_MAX_CHUNKS && rank >= 0 && rank < kPushMaxRanks && seq > 0, KTB_ERR_ARG,
+              "ktb_push_consume: bad chunk/rank arguments");
+  KTB_REQUIRE(stage_local && ctrl_local && ctrl_root_peer && (dst_root_shard || shard_elems == 0), KTB_ERR_ARG,
+              "ktb_push_consume: null argument");
+  KTB_GUARD(dev);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const MapParams p = make_params(alpha, beta);
+  uint8_t* cl = static_cast<uint8_t*>(ctrl_local);
+  const unsigned long long* ready = reinterpret_cast<const unsigned long long*>(cl + KTB_CTRL_READY);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(cl + KTB_CTRL_TICKET);
+  unsigned int* status = reinterpret_cast<unsigned int*>(cl + KTB_CTRL_STATUS);
+  unsigned long long* ack =
+      reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ctrl_root_peer) + KTB_CTRL_ACK) + rank;
+  const uint8_t* stage = static_cast<const uint8_t*>(stage_local) + (size_t)(seq & 1) * stage_stride;
+  for (int c = 0; c < n_chunks; ++c) {
+    size_t cb = 0, ce = 0;
+    chunk_bounds(shard_elems, n_chunks, c, &cb, &ce);
+    const size_t nb = (ce - cb) * es;
+    const unsigned grid = (unsigned)std::max<size_t>(1, (nb + kPushTile - 1) / kPushTile);
+    const int publish = (c == n_chunks - 1) ? 1 : 0;
+    const uint8_t* s = stage + cb * es;
+    uint8_t* d = static_cast<uint8_t*>(dst_root_shard) + cb * es;
+#define KTB_PC(DT, OPC)                                                                                       \
+  push_consume_kernel<DT, OPC><<<grid, kPushThreads, 0, st>>>(s, d, nb, p, ready + c, seq, ack, publish, ticket, status)
+    if (op == KTB_OP_IDENTITY) {
+      KTB_PC(KTB_U8, KTB_OP_IDENTITY);
+    } else {
+      switch (dtype) {
+        case KTB_F32: if (op == KTB_OP_SCALE) KTB_PC(KTB_F32, KTB_OP_SCALE); else KTB_PC(KTB_F32, KTB_OP_AFFINE); break;
+        case KTB_BF16: if (op == KTB_OP_SCALE) KTB_PC(KTB_BF16, KTB_OP_SCALE); else KTB_PC(KTB_BF16, KTB_OP_AFFINE); break;
+        case KTB_I32: if (op == KTB_OP_SCALE) KTB_PC(KTB_I32, KTB_OP_SCALE); else KTB_PC(KTB_I32, KTB_OP_AFFINE); break;
+        default: if (op == KTB_OP_SCALE) KTB_PC(KTB_I64, KTB_OP_SCALE); else KTB_PC(KTB_I64, KTB_OP_AFFINE); break;
+      }
+    }
+#undef KTB_PC
+    KTB_CK(cudaGetLastError());
+  }
+  return KTB_OK;
+}
+
+int ktb_push_wait(int root_dev, void* ctrl_root, int n_ranks, int root_rank, unsigned long long seq, uintptr_t stream) {
+  int rc = require_device(root_dev);
+  if (rc) return rc;
+  KTB_REQUIRE(ctrl_root && n_ranks > 0 && n_ranks <= kPushMaxRanks, KTB_ERR_ARG, "ktb_push_wait: bad arguments");
+  KTB_GUARD(root_dev);
+  uint8_t* croot = static_cast<uint8_t*>(ctrl_root);
+  push_wait_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const unsigned long long*>(croot + KTB_CTRL_ACK), n_ranks, root_rank, seq,
+      reinterpret_cast<unsigned int*>(croot + KTB_CTRL_STATUS));
+  KTB_CK(cudaGetLastError());
+  return KTB_OK;
+}
+
+// Reads (synchronously) the sticky timeout status of a control block: 0 = healthy.
+int ktb_push_status(int dev, const void* ctrl, unsigned int* out) {
+  int rc = require_device(dev);
+  if (rc) return rc;
+  KTB_REQUIRE(ctrl && out, KTB_ERR_ARG, "ktb_push_status: null argument");
+  KTB_GUARD(dev);
+  KTB_CK(cudaMemcpy(out, static_cast<const uint8_t*>(ctrl) + KTB_CTRL_STATUS, sizeof(unsigned int),
+                    cudaMemcpyDeviceToHost));
+  return KTB_OK;
+}
+
+}  // extern "C"

@@ -67,6 +67,13 @@ _SIGNATURES = {
     "ktb_broadcast": (c_int, [c_int, c_void_p, POINTER(c_void_p), c_int, c_size_t, c_uintptr]),
     "ktb_scatter_map_gather": (c_int, [c_int, c_int, c_void_p, c_void_p, c_size_t, c_size_t, c_double, c_double, c_int, POINTER(c_int), c_int, c_int, POINTER(c_uintptr)]),
     "ktb_scatter_map_reduce": (c_int, [c_int, c_int, c_void_p, c_size_t, c_size_t, c_double, c_double, c_int, POINTER(c_int), c_int, c_void_p, c_void_p, POINTER(c_void_p), POINTER(c_uintptr)]),
+    "ktb_push_control_bytes": (c_size_t, []),
+    "ktb_push_scatter": (c_int, [c_int, c_void_p, c_size_t, c_size_t, c_int, c_int, c_int, POINTER(c_void_p), c_size_t,
+                                 POINTER(c_void_p), c_void_p, c_int, ctypes.c_ulonglong, c_uintptr]),
+    "ktb_push_consume": (c_int, [c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_double, c_double,
+                                 c_void_p, c_void_p, c_int, c_int, ctypes.c_ulonglong, c_uintptr]),
+    "ktb_push_wait": (c_int, [c_int, c_void_p, c_int, c_int, ctypes.c_ulonglong, c_uintptr]),
+    "ktb_push_status": (c_int, [c_int, c_void_p, POINTER(ctypes.c_uint)]),
     "ktb_map_host": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_double, c_double, c_size_t, c_void_p, c_void_p]),
     "ktb_mlp_scratch_bytes": (c_size_t, [c_size_t, c_int]),
     "ktb_mlp_bf16": (c_int, [c_int, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uintptr]),

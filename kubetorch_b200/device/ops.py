@@ -377,8 +377,111 @@ def scatter_map_reduce(
     return total, partials
 
 
+class Arena:
+    """A library-owned device allocation (ktb_arena_alloc): IPC-exportable, viewable as a torch tensor."""
+
+    def __init__(self, device: int, nbytes: int, zero: bool = False):
+        ensure_init({device})
+        self.device, self.nbytes = int(device), int(nbytes)
+        p = ctypes.c_void_p()
+        L.call("ktb_arena_alloc", self.device, self.nbytes, ctypes.byref(p))
+        self.ptr = p.value
+        self._owned = True
+        if zero:
+            self.tensor(torch.uint8).zero_()
+            torch.cuda.synchronize(self.device)
+
+    def tensor(self, dtype: torch.dtype = torch.uint8, numel: Optional[int] = None, offset: int = 0) -> torch.Tensor:
+        es = torch.empty((), dtype=dtype).element_size()
+        n = (self.nbytes - offset) // es if numel is None else int(numel)
+        typestr = {torch.uint8: "|u1", torch.float32: "<f4", torch.int32: "<i4", torch.int64: "<i8",
+                   torch.bfloat16: "<u2"}[dtype]
+        holder = type("_CAI", (), {})()
+        holder.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (self.ptr + offset, False),
+                                           "version": 3}
+        t = torch.as_tensor(holder, device=f"cuda:{self.device}")
+        return t.view(torch.bfloat16) if dtype == torch.bfloat16 else t
+
+    def export(self) -> bytes:
+        h = (ctypes.c_ubyte * L.IPC_HANDLE_BYTES)()
+        L.call("ktb_ipc_export", self.device, ctypes.c_void_p(self.ptr), h)
+        return bytes(h)
+
+    def free(self):
+        if self._owned and self.ptr:
+            L.call("ktb_arena_free", self.device, ctypes.c_void_p(self.ptr))
+            self.ptr = 0
+
+
+def ipc_open(device: int, handle: bytes) -> int:
+    """Map another process's arena on `device`; returns the device pointer."""
+    ensure_init({device})
+    h = (ctypes.c_ubyte * L.IPC_HANDLE_BYTES).from_buffer_copy(handle)
+    p = ctypes.c_void_p()
+    L.call("ktb_ipc_open", int(device), h, ctypes.byref(p))
+    return p.value
+
+
+class PushSession:
+    """Push/push scatter → exec → gather driven by ONE controller process over distinct GPUs
+    (ktb_push_*): the root's kernel pushes shard pieces into each rank's staging buffer, each rank's
+    kernel waits in-kernel for its piece, maps it and pushes the result into the root's result
+    buffer. No events between devices: flags in device memory order everything."""
+
+    def __init__(self, devices: Sequence[int], max_shard_bytes: int, n_chunks: int = 8):
+        self.devices = [int(d) for d in devices]
+        ensure_init(set(self.devices))
+        self.root = self.devices[0]
+        self.n_chunks = int(n_chunks)
+        self.stride = (int(max_shard_bytes) + 255) // 256 * 256
+        cb = L.load().ktb_push_control_bytes()
+        self.ctrl = [torch.zeros(cb, dtype=torch.uint8, device=f"cuda:{d}") for d in self.devices]
+        self.stage = [None if r == 0 else torch.empty(2 * self.stride, dtype=torch.uint8, device=f"cuda:{d}")
+                      for r, d in enumerate(self.devices)]
+        for d in set(self.devices):
+            torch.cuda.synchronize(d)
+        self.seq = 0
+        n = len(self.devices)
+        self._stage_ptrs = L.arr(ctypes.c_void_p, [0 if s is None else s.data_ptr() for s in self.stage])
+        self._ctrl_ptrs = L.arr(ctypes.c_void_p, [c.data_ptr() for c in self.ctrl])
+        self._n = n
+
+    def call(self, x_root: torch.Tensor, out_root: torch.Tensor, op: str, alpha: float = 1.0, beta: float = 0.0):
+        self.seq += 1
+        seq, n, es = self.seq, self._n, x_root.element_size()
+        gran = row_elems(x_root)
+        rows = x_root.numel() // gran
+        dt = dtype_code(x_root.dtype)
+        root_stream = _stream(self.root, None)
+        L.call("ktb_push_scatter", self.root, x_root.data_ptr(), x_root.numel(), gran, dt, n, 0, self._stage_ptrs,
+               self.stride, self._ctrl_ptrs, self.ctrl[0].data_ptr(), self.n_chunks, seq, root_stream)
+        for r in range(1, n):
+            b, e = shard_bounds(rows, n, r)
+            if (e - b) * gran * es > self.stride:
+                raise ValueError("shard larger than the session's staging buffers")
+            L.call("ktb_push_consume", self.devices[r], OPS[op], dt, self.stage[r].data_ptr(), self.stride,
+                   out_root.data_ptr() + b * gran * es, (e - b) * gran, float(alpha), float(beta),
+                   self.ctrl[r].data_ptr(), self.ctrl[0].data_ptr(), r, self.n_chunks, seq,
+                   _stream(self.devices[r], None))
+        b, e = shard_bounds(rows, n, 0)  # the root's own shard, on the root's HBM
+        if e > b:
+            L.call("ktb_map", self.root, OPS[op], dt, x_root.data_ptr() + b * gran * es,
+                   out_root.data_ptr() + b * gran * es, (e - b) * gran, float(alpha), float(beta), L.VARIANT_AUTO,
+                   root_stream)
+        L.call("ktb_push_wait", self.root, self.ctrl[0].data_ptr(), n, 0, seq, root_stream)
+        return out_root
+
+    def check(self):
+        for d, c in zip(self.devices, self.ctrl):
+            st = ctypes.c_uint(0)
+            L.call("ktb_push_status", d, c.data_ptr(), ctypes.byref(st))
+            if st.value:
+                raise RuntimeError(f"push pipeline: an in-kernel wait timed out on cuda:{d}")
+
+
 # ---- host-resident args ------------------------------------------------------------------------------
 _stage_cache = {}
+_host_locks = {}
 
 
 def map_host(
@@ -388,7 +491,7 @@ def map_host(
     beta: float = 0.0,
     out_host: Optional[torch.Tensor] = None,
     device: int = 0,
-    chunk_bytes: int = 8 << 20,
+    chunk_bytes: int = 16 << 20,
 ) -> torch.Tensor:
     """out_host = op(x_host), both pinned host tensors; H2D, kernel and D2H of successive chunks overlap."""
     require_cuda()
@@ -400,17 +503,22 @@ def map_host(
         raise ValueError("out_host must be a pinned host tensor")
     ensure_init({device})
     key = (device, chunk_bytes)
-    st = _stage_cache.get(key)
-    if st is None:
-        st = (
-            torch.empty(2 * chunk_bytes, dtype=torch.uint8, device=f"cuda:{device}"),
-            torch.empty(2 * chunk_bytes, dtype=torch.uint8, device=f"cuda:{device}"),
+    # one host-path call at a time per device: the staging buffers and the library's three copy/exec
+    # streams are per-device (the PCIe link serialises them anyway)
+    with _init_lock:
+        lock = _host_locks.setdefault(device, threading.Lock())
+    with lock:
+        st = _stage_cache.get(key)
+        if st is None:
+            st = (
+                torch.empty(2 * chunk_bytes, dtype=torch.uint8, device=f"cuda:{device}"),
+                torch.empty(2 * chunk_bytes, dtype=torch.uint8, device=f"cuda:{device}"),
+            )
+            _stage_cache[key] = st
+        L.call(
+            "ktb_map_host", device, OPS[op], dtype_code(x_host.dtype), x_host.data_ptr(), out_host.data_ptr(),
+            x_host.numel(), float(alpha), float(beta), chunk_bytes, st[0].data_ptr(), st[1].data_ptr(),
         )
-        _stage_cache[key] = st
-    L.call(
-        "ktb_map_host", device, OPS[op], dtype_code(x_host.dtype), x_host.data_ptr(), out_host.data_ptr(),
-        x_host.numel(), float(alpha), float(beta), chunk_bytes, st[0].data_ptr(), st[1].data_ptr(),
-    )
     return out_host
 
 

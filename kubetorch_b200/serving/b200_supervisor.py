@@ -31,7 +31,8 @@ from .process_worker import instantiate, load_callable, resolve_method
 class B200Supervisor:
     def __init__(self, pointers=None, init_args=None, name: str = None, devices: Optional[List[int]] = None,
                  num_proc=None, distributed: bool = True, allowed_serialization: str = "json,pickle",
-                 host_chunk_bytes: int = 8 << 20, variant: int = 0, callable_obj=None, **extra):
+                 host_chunk_bytes: int = 16 << 20, variant: int = 0, callable_obj=None, transfer: str = "auto",
+                 **extra):
         self.pointers, self.init_args, self.name = pointers, init_args, name
         self.callable_obj = callable_obj
         self.devices = list(devices) if devices is not None else None
@@ -44,6 +45,11 @@ class B200Supervisor:
         self._host_pool: Optional[ThreadPoolExecutor] = None
         self._pin_cache = {}
         self._lock = threading.Lock()
+        self._host_lock = threading.Lock()
+        self._push = None
+        if transfer not in ("auto", "pull", "push"):
+            raise ValueError("transfer must be 'auto', 'pull' or 'push'")
+        self.transfer = transfer
         self.config_hash = hash(("b200", tuple(self.devices or ()), num_proc, distributed))
 
     # ---- lifecycle ------------------------------------------------------------------------------------
@@ -76,6 +82,7 @@ class B200Supervisor:
             self._host_pool.shutdown(wait=False)
             self._host_pool = None
         self._pin_cache.clear()
+        self._push = None
 
     @property
     def world_size(self) -> int:
@@ -137,7 +144,17 @@ class B200Supervisor:
         x = x.contiguous()
         with torch.cuda.device(root):
             out = torch.empty_like(x)
-        ops.scatter_map_gather(x, op, alpha, beta, devices=self.devices, out_root=out, variant=self.variant)
+        distinct = len(set(self.devices)) == len(self.devices) and len(self.devices) > 1
+        if self.transfer == "push" or (self.transfer == "auto" and distinct and x.numel() * x.element_size() >= (8 << 20)):
+            # push/push flag pipeline: both NVLink directions carry posted writes (see ktb_push.cu)
+            with self._lock:
+                rows = x.shape[0]
+                shard_bytes = ops.shard_bounds(rows, self.world_size, 0)[1] * ops.row_elems(x) * x.element_size()
+                if self._push is None or self._push.stride < shard_bytes:
+                    self._push = ops.PushSession(self.devices, shard_bytes)
+                self._push.call(x, out, op, alpha, beta)
+        else:
+            ops.scatter_map_gather(x, op, alpha, beta, devices=self.devices, out_root=out, variant=self.variant)
         return self._shard_views(out, x)
 
     def _pinned(self, key, like):
@@ -155,6 +172,12 @@ class B200Supervisor:
         if x.dim() == 0:
             x = x.reshape(1)
         x = x.contiguous()
+        with self._host_lock:  # the pinned staging tensors are per deployment
+            return self._host_map_locked(x, op, alpha, beta)
+
+    def _host_map_locked(self, x, op, alpha, beta):
+        from ..device import ops
+
         if not x.is_pinned():
             staged = self._pinned("in", x)
             staged.copy_(x)  # page-locking copy: the caller handed us pageable memory

@@ -138,6 +138,13 @@ def test_two_gpu_peer_path_matches_oracle():
         y = ops.scatter_map_gather(x.cuda(0), "affine", 0.5, 1.5, devices=[0, 1], variant=variant)
         torch.cuda.synchronize(0)
         assert torch.equal(y.cpu(), want), variant
+    sess = ops.PushSession([0, 1], ops.shard_bounds(x.numel(), 2, 0)[1] * 4)
+    for it in range(4):  # consecutive calls exercise staging parity and the ack back-pressure
+        y = torch.zeros_like(x, device="cuda:0")
+        sess.call(x.cuda(0), y, "affine", 0.5, 1.5)
+        torch.cuda.synchronize(0)
+        assert torch.equal(y.cpu(), want), ("push", it)
+    sess.check()
     xi = torch.randint(-(2**40), 2**40, (100_003,), dtype=torch.int64)
     total, partials = ops.scatter_map_reduce(xi.cuda(0), "identity", devices=[0, 1])
     assert partials.tolist() == ref_dispatch.spmd_call(cases.shard_sum, xi, num_proc=2, serialization="pickle")

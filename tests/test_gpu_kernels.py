@@ -282,3 +282,24 @@ def test_mlp_tcgen05_matches_recorded_reference_and_fp32(K, golden):
     top2 = want2.topk(2, dim=1).values
     clear = (top2[:, 0] - top2[:, 1]) > 2**-6
     assert torch.equal(got2.argmax(1)[clear], want2.argmax(1)[clear])
+
+
+def test_push_pipeline_emulated_on_one_gpu(K):
+    """push/push flag pipeline with all ranks time-sliced on cuda:0 (same stream → root first): same results
+    as the oracle, across consecutive calls (staging parity + ack back-pressure) and ragged shards."""
+    for n_ranks, n in ((4, 1 << 20), (3, 1003), (8, (1 << 22) + 77), (2, 5)):
+        x = _rand(torch.float32, n, seed=n).cuda()
+        sess = K.PushSession([0] * n_ranks, K.shard_bounds(n, n_ranks, 0)[1] * 4, n_chunks=4)
+        for it in range(5):
+            a, b = 0.5 + it, 1.0 - it
+            y = torch.zeros_like(x)
+            sess.call(x, y, "affine", a, b)
+            torch.cuda.synchronize()
+            assert torch.equal(y.cpu(), x.cpu() * a + b), (n_ranks, n, it)
+        sess.check()
+    xi = _rand(torch.int64, 70_001).cuda()
+    sess = K.PushSession([0, 0, 0], K.shard_bounds(70_001, 3, 0)[1] * 8, n_chunks=8)
+    yi = torch.zeros_like(xi)
+    sess.call(xi, yi, "scale", -3)
+    torch.cuda.synchronize()
+    assert torch.equal(yi.cpu(), xi.cpu() * -3)
