@@ -174,8 +174,10 @@ def run_ours(args):
         assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     dev = local_rank if world > 1 else 0
     torch.cuda.set_device(dev)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device(f"cuda:{dev}"))
+        cpu_group = dist.new_group(backend="gloo")  # host-side waits must not spin on a GPU
     n_gpus = world if world > 1 else args.gpus
     K, W = args.steps, max(args.warmup, 3)
     L.load()
@@ -352,7 +354,7 @@ def run_ours(args):
                        "H2D/kernel/D2H over each GPU's own PCIe link, host-clock timed"}
         remote.teardown()
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=cpu_group)  # other ranks wait on the CPU while rank 0 drives all N GPUs
 
     # ---- CPU baseline (N=1 only), bounded sample ---------------------------------------------------------------------
     cpu = None

@@ -141,6 +141,7 @@ int ktb_scatter_map_gather(int op, int dtype, const void* src_root, void* dst_ro
     return streams ? reinterpret_cast<cudaStream_t>(streams[r]) : device_info(devs[r])->stream_rank;
   };
   cudaStream_t root_stream = stream_of(root_rank);
+  bool joined[kMaxDevices] = {false};
   {
     KTB_GUARD(root_dev);
     KTB_CK(cudaEventRecord(root->ev_a, root_stream));  // args are ready on the root
@@ -162,10 +163,16 @@ int ktb_scatter_map_gather(int op, int dtype, const void* src_root, void* dst_ro
                     static_cast<uint8_t*>(dst_root) + b * es, e - b, p, variant, st);
     if (rc) return rc;
     if (!is_root) {
-      DeviceInfo* di = device_info(dev);
-      KTB_CK(cudaEventRecord(di->ev_b, st));
-      KTB_CK(cudaStreamWaitEvent(root_stream, di->ev_b, 0));  // gather complete → visible to the root
+      KTB_CK(cudaEventRecord(device_info(dev)->ev_b, st));
+      joined[r] = true;
     }
+  }
+  // Join on the root stream with the ROOT device current: stream handle 0 names the default stream of
+  // whichever device is current, so the wait must be issued under the root's guard.
+  {
+    KTB_GUARD(root_dev);
+    for (int r = 0; r < n_ranks; ++r)
+      if (joined[r]) KTB_CK(cudaStreamWaitEvent(root_stream, device_info(devs[r])->ev_b, 0));
   }
   return KTB_OK;
 }
@@ -191,6 +198,7 @@ int ktb_scatter_map_reduce(int op, int dtype, const void* src_root, size_t n_ele
     return streams ? reinterpret_cast<cudaStream_t>(streams[r]) : device_info(devs[r])->stream_rank;
   };
   cudaStream_t root_stream = stream_of(root_rank);
+  bool joined[kMaxDevices] = {false};
   {
     KTB_GUARD(root_dev);
     KTB_CK(cudaEventRecord(root->ev_a, root_stream));
@@ -213,12 +221,13 @@ int ktb_scatter_map_reduce(int op, int dtype, const void* src_root, size_t n_ele
                            static_cast<uint8_t*>(partials_root) + (size_t)r * acc_size, workspaces[r], st);
     if (rc) return rc;
     if (!is_root) {
-      DeviceInfo* di = device_info(dev);
-      KTB_CK(cudaEventRecord(di->ev_b, st));
-      KTB_CK(cudaStreamWaitEvent(root_stream, di->ev_b, 0));
+      KTB_CK(cudaEventRecord(device_info(dev)->ev_b, st));
+      joined[r] = true;
     }
   }
   KTB_GUARD(root_dev);
+  for (int r = 0; r < n_ranks; ++r)
+    if (joined[r]) KTB_CK(cudaStreamWaitEvent(root_stream, device_info(devs[r])->ev_b, 0));
   return launch_reduce_partials(root_dev, dtype, partials_root, n_ranks, out_root, root_stream);
 }
 
