@@ -20,6 +20,7 @@
 namespace ktb {
 
 extern int g_red_ctas_per_sm;  // ktb_reduce.cu
+extern int g_mlp_persistent;   // ktb_mlp.cu
 
 // ---- tunables (ktb_set_tuning) ---------------------------------------------------------------
 static std::atomic<int> g_vec_ctas_per_sm{0};  // 0 = one tile per CTA (measured best, profiles/r1_sweep.md)
@@ -353,6 +354,7 @@ int ktb_set_tuning(int key, int value) {
     case 4: g_vec_flavor = value; return KTB_OK;
     case 5: g_vec_unroll = value; return KTB_OK;
     case 6: g_red_ctas_per_sm = value > 0 ? value : 8; return KTB_OK;
+    case 7: g_mlp_persistent = value ? 1 : 0; return KTB_OK;
     case 3:
       KTB_REQUIRE(value >= KTB_VARIANT_VEC && value <= KTB_VARIANT_SCALAR, KTB_ERR_ARG,
                   "ktb_set_tuning: bad auto variant %d", value);

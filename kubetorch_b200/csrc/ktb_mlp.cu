@@ -29,7 +29,8 @@ constexpr int kMlpBlockM = 128;
 constexpr int kMlpBlockK = 64;   // 64 bf16 = 128 bytes = one SWIZZLE_128B row
 constexpr int kMlpUmmaK = 16;
 constexpr int kMlpThreads = 192;
-constexpr size_t kMlpChunkRows = 16384;  // 2 x 32 MiB of hidden activations per chunk (d_hidden = 1024)
+constexpr size_t kMlpChunkRows = 16384;
+int g_mlp_persistent = 1;  // ktb_set_tuning key 7: 1 = persistent double-buffered kernel, 0 = one tile per CTA  // 2 x 32 MiB of hidden activations per chunk (d_hidden = 1024)
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -41,6 +42,9 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
 }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -107,7 +111,7 @@ struct MlpSmem {
   static constexpr int kBBytes = BLOCK_N * kMlpBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarrierOff = STAGES * kStageBytes;
-  static constexpr int kTotal = kBarrierOff + (2 * STAGES + 1) * 8 + 16 + 1024 /* alignment slack */;
+  static constexpr int kTotal = kBarrierOff + (2 * STAGES + 4) * 8 + 16 + 1024 /* alignment slack */;
 };
 
 // C[m0:m0+128, n0:n0+BLOCK_N] = act(A[m0:.., :K] · B[n0:.., :K]ᵀ), one output tile per CTA.
@@ -218,6 +222,133 @@ __global__ void __launch_bounds__(kMlpThreads)
   }
 }
 
+// Persistent form: one CTA per SM loops over output tiles (n fastest, so the CTAs running at the same
+// time share A rows in L2); the fp32 accumulator is DOUBLE-BUFFERED in TMEM (2 x BLOCK_N columns) so the
+// epilogue of tile t (tcgen05.ld → ReLU → bf16 → global) overlaps the TMA/MMA main loop of tile t+1.
+//   tmem_full[a]  : MMA warp → epilogue   (tcgen05.commit, count 1)
+//   tmem_empty[a] : epilogue → MMA warp   (one arrive per epilogue warp, count 4)
+template <int BLOCK_N, int STAGES, bool RELU>
+__global__ void __launch_bounds__(kMlpThreads)
+    gemm_bf16_tn_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                   __nv_bfloat16* __restrict__ C, int ldc, int K, int tiles_m, int tiles_n) {
+  using S = MlpSmem<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarrierOff);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;        // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = K / kMlpBlockK;
+  const int num_tiles = tiles_m * tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 4);
+    mbar_init(&tmem_empty[1], 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, 2 * BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;  // running k-block counter across tiles → stage / parity
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * kMlpBlockM;
+        const int n0 = (tile % tiles_n) * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+          uint8_t* a_dst = smem + (size_t)s * S::kStageBytes;
+          mbar_expect_tx(&full[s], S::kStageBytes);
+          tma_load_2d(a_dst, &map_a, kb * kMlpBlockK, m0, &full[s]);
+          tma_load_2d(a_dst + S::kABytes, &map_b, kb * kMlpBlockK, n0, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kMlpBlockM, BLOCK_N);
+      int it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const int as = t & 1;
+        mbar_wait(&tmem_empty[as], ((t >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint8_t* a_src = smem + (size_t)s * S::kStageBytes;
+          const uint64_t adesc = make_smem_desc_sw128(a_src);
+          const uint64_t bdesc = make_smem_desc_sw128(a_src + S::kABytes);
+#pragma unroll
+          for (int k = 0; k < kMlpBlockK / kMlpUmmaK; ++k)
+            umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int as = t & 1;
+      const int m0 = (tile / tiles_n) * kMlpBlockM;
+      const int n0 = (tile % tiles_n) * BLOCK_N;
+      mbar_wait(&tmem_full[as], (t >> 1) & 1);
+      tc_fence_after();
+      __nv_bfloat16* crow = C + (size_t)(m0 + quarter * 32 + lane) * ldc + n0;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c), acc);
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float lo = __uint_as_float(acc[2 * j]);
+          float hi = __uint_as_float(acc[2 * j + 1]);
+          if (RELU) {
+            lo = fmaxf(lo, 0.f);
+            hi = fmaxf(hi, 0.f);
+          }
+          __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+          packed[j] = *reinterpret_cast<uint32_t*>(&v);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(crow + c);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);  // this warp's quarter of the accumulator is free
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BLOCK_N);
+  }
+}
+
 // ---- host side --------------------------------------------------------------------------------------
 typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -259,10 +390,21 @@ static int launch_gemm(const void* A, const void* B, void* C, size_t M, int N, i
   if (rc) return rc;
   rc = make_map(&mb, B, (uint64_t)N, (uint64_t)K, BLOCK_N);
   if (rc) return rc;
-  auto kfn = gemm_bf16_tn_kernel<BLOCK_N, STAGES, RELU>;
-  KTB_CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-  dim3 grid((unsigned)(M / kMlpBlockM), (unsigned)(N / BLOCK_N));
-  kfn<<<grid, kMlpThreads, S::kTotal, stream>>>(ma, mb, static_cast<__nv_bfloat16*>(C), ldc, K);
+  if (g_mlp_persistent) {
+    auto kfn = gemm_bf16_tn_persistent_kernel<BLOCK_N, STAGES, RELU>;
+    KTB_CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    const int tiles_m = (int)(M / kMlpBlockM), tiles_n = N / BLOCK_N;
+    int dev = 0;
+    KTB_CK(cudaGetDevice(&dev));
+    const int sms = device_info(dev) ? device_info(dev)->sm_count : 148;
+    const int grid = std::min(tiles_m * tiles_n, sms);
+    kfn<<<grid, kMlpThreads, S::kTotal, stream>>>(ma, mb, static_cast<__nv_bfloat16*>(C), ldc, K, tiles_m, tiles_n);
+  } else {
+    auto kfn = gemm_bf16_tn_kernel<BLOCK_N, STAGES, RELU>;
+    KTB_CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    dim3 grid((unsigned)(M / kMlpBlockM), (unsigned)(N / BLOCK_N));
+    kfn<<<grid, kMlpThreads, S::kTotal, stream>>>(ma, mb, static_cast<__nv_bfloat16*>(C), ldc, K);
+  }
   KTB_CK(cudaGetLastError());
   return KTB_OK;
 }
