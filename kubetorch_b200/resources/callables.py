@@ -200,8 +200,12 @@ class Module:
             extra = {k: v for k, v in dist.items()
                      if k not in ("distribution_type", "workers", "quorum_workers", "num_proc", "port",
                                   "quorum_timeout", "monitor_members")}
+            gpu = bool(compute.gpus) and backend != "cpu"
+            devices = extra.pop("devices", None)
+            extra.pop("transfer", None)
             return dict(distribution_type=dtype, workers=workers, num_proc=num_proc, port=dist.get("port"),
-                        env_vars={k: str(v) for k, v in compute.env_vars.items()}, **extra, **common)
+                        env_vars={k: str(v) for k, v in compute.env_vars.items()}, gpu_arenas=gpu,
+                        devices=devices, **extra, **common)
         if dtype not in (None, "local"):
             return dict(distribution_type=dtype, **common)  # factory raises the reference's error text
         return dict(distribution_type="local", callable_obj=target, **common)

@@ -23,7 +23,8 @@ from .process_worker import SHUTDOWN, worker_main
 class ProcessPool:
     def __init__(self, num_processes: int, pointers, init_args, name: str, max_threads_per_proc: int = 10,
                  base_env: Optional[Dict[str, str]] = None, allowed_serialization: str = "json,pickle",
-                 pod_names: Optional[List[str]] = None, start_timeout: float = 300.0):
+                 pod_names: Optional[List[str]] = None, start_timeout: float = 300.0,
+                 gpu_cfgs: Optional[List[dict]] = None):
         self.num_processes = int(num_processes)
         self.name = name
         self._ctx = mp.get_context("spawn")  # like the reference (execution_supervisor.py:66-67)
@@ -34,6 +35,7 @@ class ProcessPool:
         self._lock = threading.Lock()
         self._ids = itertools.count()
         self._closed = False
+        self.full_replies = bool(gpu_cfgs)  # GPU ranks attach arena metadata to their replies
         self.pod_names = pod_names or [f"{name}-rank{i}" for i in range(self.num_processes)]
         ready: List[Future] = []
         for i in range(self.num_processes):
@@ -42,7 +44,8 @@ class ProcessPool:
             env.setdefault("POD_NAME", self.pod_names[i])
             p = self._ctx.Process(
                 target=worker_main,
-                args=(child, i, pointers, init_args, name, max_threads_per_proc, env, allowed_serialization),
+                args=(child, i, pointers, init_args, name, max_threads_per_proc, env, allowed_serialization,
+                      gpu_cfgs[i] if gpu_cfgs else None),
                 daemon=True, name=f"ktb-worker-{name}-{i}",
             )
             p.start()
@@ -90,7 +93,7 @@ class ProcessPool:
                 if fut is None:
                     continue
                 if msg["ok"]:
-                    fut.set_result(msg["result"])
+                    fut.set_result(msg if self.full_replies else msg["result"])
                 else:
                     fut.set_exception(rebuild_exception(msg["envelope"]))
 
@@ -110,7 +113,7 @@ class ProcessPool:
 
     # ---- calls ----------------------------------------------------------------------------------------
     def submit(self, idx: int, payload: bytes, method_name: Optional[str], env: Dict[str, str],
-               serialization: str) -> Future:
+               serialization: str, extra: Optional[dict] = None) -> Future:
         """Send one request to worker idx. `payload` = pickle.dumps((args, kwargs)) made once by the caller."""
         fut: Future = Future()
         rid = next(self._ids)
@@ -121,6 +124,8 @@ class ProcessPool:
             self._pending[rid] = fut
             self._pending_owner[rid] = idx
         req = {"id": rid, "payload": payload, "method": method_name, "env": env, "serialization": serialization}
+        if extra:
+            req.update(extra)
         try:
             self._conns[idx].send_bytes(pickle.dumps(req, protocol=5))
         except (OSError, ValueError):
@@ -128,9 +133,9 @@ class ProcessPool:
         return fut
 
     def call_all(self, payload: bytes, method_name: Optional[str], envs: List[Dict[str, str]], serialization: str,
-                 ranks: Optional[List[int]] = None) -> List[Future]:
+                 ranks: Optional[List[int]] = None, extras: Optional[Dict[int, dict]] = None) -> List[Future]:
         ranks = list(range(self.num_processes)) if ranks is None else ranks
-        return [self.submit(i, payload, method_name, envs[i], serialization) for i in ranks]
+        return [self.submit(i, payload, method_name, envs[i], serialization, (extras or {}).get(i)) for i in ranks]
 
     def stop(self):
         if self._closed:

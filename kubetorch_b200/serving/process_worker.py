@@ -67,11 +67,70 @@ def validate_result(result: Any, serialization: str):
     return result
 
 
+class _GpuArenas:
+    """Rank-side view of the coordinator-owned HBM arenas (CUDA IPC): tensor args arrive as zero-copy views
+    of the arg arena, tensor results leave through the result arena (ktb_pack)."""
+
+    def __init__(self, cfg: dict):
+        import torch
+
+        from ..device import ops
+
+        self.device = int(cfg["device"])
+        torch.cuda.set_device(self.device)
+        ops.ensure_init([self.device])
+        self.ops = ops
+        self.torch = torch
+        self.arg_ptr = self.res_ptr = 0
+        self.arg_bytes = self.res_bytes = 0
+        self.update(cfg)
+
+    def update(self, cfg: dict):
+        if cfg.get("arg_handle") is not None:
+            self.arg_ptr, self.arg_bytes = self.ops.ipc_open(self.device, cfg["arg_handle"]), int(cfg["arg_bytes"])
+        if cfg.get("res_handle") is not None:
+            self.res_ptr, self.res_bytes = self.ops.ipc_open(self.device, cfg["res_handle"]), int(cfg["res_bytes"])
+
+    def _view(self, ptr: int, dtype_name: str, shape, offset: int):
+        torch = self.torch
+        dtype = getattr(torch, dtype_name)
+        numel = 1
+        for d in shape:
+            numel *= d
+        typestr = {"uint8": "|u1", "int8": "|i1", "float32": "<f4", "float64": "<f8", "int32": "<i4", "int64": "<i8",
+                   "float16": "<f2", "bfloat16": "<u2", "bool": "|u1", "int16": "<i2"}[dtype_name]
+        holder = type("_CAI", (), {})()
+        holder.__cuda_array_interface__ = {"shape": (max(numel, 1),), "typestr": typestr,
+                                           "data": (ptr + offset, False), "version": 3}
+        t = torch.as_tensor(holder, device=f"cuda:{self.device}")[:numel]
+        if dtype in (torch.bfloat16, torch.bool):
+            t = t.view(dtype)
+        return t.reshape(shape)
+
+    def arg_views(self, refs, offsets):
+        return [self._view(self.arg_ptr, r.dtype, r.shape, off) for r, off in zip(refs, offsets)]
+
+    def pack_results(self, leaves):
+        """Pack result leaves into the result arena. Returns offsets, or None if the arena is too small."""
+        torch, ops = self.torch, self.ops
+        leaves = [t.contiguous() for t in leaves]
+        nbytes = [t.numel() * t.element_size() for t in leaves]
+        offsets, total = ops.pack_layout(nbytes)
+        if total > self.res_bytes:
+            return None, total
+        arena = self._view(self.res_ptr, "uint8", (self.res_bytes,), 0)
+        ops.pack(leaves, arena=arena)
+        torch.cuda.current_stream(self.device).synchronize()  # results are in HBM before the reply leaves
+        return offsets, total
+
+
 def worker_main(conn, local_rank: int, pointers, init_args, name: str, max_threads: int, base_env: Dict[str, str],
-                allowed_serialization: str):
+                allowed_serialization: str, gpu_cfg: Optional[dict] = None):
     os.environ["LOCAL_RANK"] = str(local_rank)  # also set at construction in the reference (process_worker.py:33)
     os.environ.update(base_env)
     send_lock = threading.Lock()
+    arena_lock = threading.Lock()
+    state = {"arenas": None}
 
     def reply(msg: dict):
         data = pickle.dumps(msg, protocol=5)
@@ -95,6 +154,22 @@ def worker_main(conn, local_rank: int, pointers, init_args, name: str, max_threa
             os.environ.update(req.get("env") or {})
             check_allowed(req["serialization"], allowed_serialization)
             args, kwargs = pickle.loads(req["payload"])
+            if gpu_cfg is not None and req.get("arena_update"):
+                with arena_lock:
+                    if state["arenas"] is None:  # CUDA is touched by the framework only when tensors travel
+                        state["arenas"] = _GpuArenas({**gpu_cfg, **req["arena_update"]})
+                    else:
+                        state["arenas"].update(req["arena_update"])
+            arenas = state["arenas"]
+            if arenas is not None:
+                from .tensor_wire import collect_refs, join_tensors
+
+                refs = []
+                collect_refs((args, kwargs), refs)
+                if refs:
+                    refs.sort(key=lambda r: r.index)
+                    views = arenas.arg_views(refs, req["arg_offsets"])
+                    args, kwargs = join_tensors((args, kwargs), views)
             method = resolve_method(callable_obj, name, req.get("method"))
             if inspect.iscoroutinefunction(method):
                 result = asyncio.run_coroutine_threadsafe(method(*args, **kwargs), loop).result()
@@ -104,12 +179,24 @@ def worker_main(conn, local_rank: int, pointers, init_args, name: str, max_threa
                     async def _await(x):
                         return await x
                     result = asyncio.run_coroutine_threadsafe(_await(result), loop).result()
+            extra = {}
+            if arenas is not None and req["serialization"] != "json":
+                from .tensor_wire import split_tensors
+
+                leaves = []
+                skeleton = split_tensors(result, leaves, lambda t: t.is_cuda and t.device.index == arenas.device)
+                if leaves:
+                    offsets, total = arenas.pack_results(leaves)
+                    if offsets is not None:
+                        result, extra = skeleton, {"res_offsets": offsets, "res_bytes": total}
+                    else:
+                        extra = {"res_needed": total}  # arena too small: this reply travels pickled, next one fits
             validate_result(result, req["serialization"])
             try:
                 payload = pickle.dumps(result, protocol=5)
             except Exception as e:  # noqa: BLE001
                 raise SerializationError(f"Result could not be serialized with pickle: {e}")
-            reply({"id": req["id"], "ok": True, "result": payload})
+            reply({"id": req["id"], "ok": True, "result": payload, **extra})
         except BaseException as e:  # noqa: BLE001
             reply({"id": req["id"], "ok": False, "envelope": package_exception(e)})
 

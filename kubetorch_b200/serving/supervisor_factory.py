@@ -20,5 +20,10 @@ def supervisor_factory(distribution_type, *args, **kwargs):
         )
     if distribution_type is None or distribution_type in SPMD_TYPES:
         dt = "tensorflow" if distribution_type == "tf" else (distribution_type or "spmd")
+        if kwargs.pop("gpu_arenas", False):
+            from .gpu_spmd import GpuSPMDSupervisor
+
+            return GpuSPMDSupervisor(distribution_type=dt, *args, **kwargs)
+        kwargs.pop("devices", None)
         return SPMDSupervisor(distribution_type=dt, *args, **kwargs)
     raise ValueError(f"Unsupported distribution type: {distribution_type}")

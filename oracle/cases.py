@@ -134,3 +134,10 @@ def all_reduce_rank():
     t = torch.tensor([float(os.environ["RANK"])])
     torch.distributed.all_reduce(t)
     return float(t.item())
+
+
+def mixed_payload(x, meta, scale=1):
+    """Arbitrary Python over a pytree of tensors and plain objects (no registered kernel):
+    returns this rank's view of the inputs."""
+    r, w = _rank_world()
+    return {"rank": r, "sum": x.sum() * scale, "y": meta["t"] + r, "tag": meta["tag"], "shape": list(x.shape)}
