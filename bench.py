@@ -29,6 +29,13 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
+
+def _clone(fn):
+    """A copy of an oracle callable to decorate (the shared function object stays undecorated)."""
+    import types
+
+    return types.FunctionType(fn.__code__, fn.__globals__, fn.__name__, fn.__defaults__, fn.__closure__)
+
 N_ELEMS = 1 << 26  # 64 Mi fp32 = 256 MiB
 METRIC = "parallel_map_arg_plus_result_GBps"
 UNIT = "GB/s"
@@ -336,7 +343,7 @@ def run_ours(args):
     # ---- e2e: public API, host buffers ---------------------------------------------------------------------------
     e2e = None
     if rank == 0:
-        double = kt.mapped("scale", alpha=2.0)(cases.double)
+        double = kt.mapped("scale", alpha=2.0)(_clone(cases.double))
         remote = kt.fn(double, name="bench-double").to(
             kt.Compute(gpus=n_gpus).distribute("b200", workers=1, num_proc=n_gpus))
         xh = torch.randn(N_ELEMS, dtype=torch.float32).pin_memory()

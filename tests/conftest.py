@@ -30,3 +30,17 @@ def golden():
 
 def resolve_args(fx, arg_spec):
     return [fx["all_inputs"][a[1:]] if isinstance(a, str) and a.startswith("@") else a for a in arg_spec]
+
+
+def mapped_copy(fn, *a, **k):
+    """@kt.mapped applied to a COPY of fn, so shared oracle callables are never mutated by a test."""
+    import functools
+    import types
+
+    import kubetorch_b200 as kt
+
+    clone = types.FunctionType(fn.__code__, fn.__globals__, fn.__name__, fn.__defaults__, fn.__closure__)
+    clone = functools.update_wrapper(clone, fn)
+    clone.__dict__.pop("__ktb_mapped__", None)
+    del clone.__wrapped__
+    return kt.mapped(*a, **k)(clone)

@@ -77,7 +77,9 @@ def test_device_backend_has_no_cpu_fallback():
     import kubetorch_b200 as kt
     from oracle import cases
 
-    double = kt.mapped("scale", alpha=2.0)(cases.double)
+    from conftest import mapped_copy
+
+    double = mapped_copy(cases.double, "scale", alpha=2.0)
     with pytest.raises(Exception) as ei:
         kt.fn(double, name="no-gpu").to(kt.Compute(gpus=1))
     assert "CUDA" in str(ei.value) or "cuda" in str(ei.value)

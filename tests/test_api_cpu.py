@@ -223,3 +223,37 @@ def test_compute_and_distribute_config_surface():
         kt.fn(cases.summer, name="bad").to(kt.Compute(cpus=1).distribute("mpi"))
     for name in ("PodTerminatedError", "WorkerMembershipChanged", "StartupError", "ImagePullError"):
         assert name in kt.EXCEPTION_REGISTRY and kt.EXCEPTION_REGISTRY[name].__module__ == "kubetorch_b200"
+
+
+def test_tensor_wire_split_and_join_roundtrip():
+    import pickle
+
+    from kubetorch_b200.serving.tensor_wire import TensorRef, collect_refs, join_tensors, split_tensors
+
+    a, b = torch.arange(6.0).reshape(2, 3), torch.ones(4, dtype=torch.int64)
+    payload = ([a, 3, "s"], {"k": (b, {"deep": a}), "n": None})
+    leaves = []
+    skel = split_tensors(payload, leaves, lambda t: True)
+    assert len(leaves) == 3 and leaves[0] is a and leaves[1] is b
+    skel2 = pickle.loads(pickle.dumps(skel))  # the header is what crosses the pipe
+    refs = []
+    collect_refs(skel2, refs)
+    assert [(r.index, r.dtype, r.shape) for r in refs] == [(0, "float32", (2, 3)), (1, "int64", (4,)), (2, "float32", (2, 3))]
+    back = join_tensors(skel2, leaves)
+    assert back[0][1:] == [3, "s"] and back[0][0] is a and back[1]["k"][0] is b and back[1]["k"][1]["deep"] is a
+    assert isinstance(skel[0][0], TensorRef) and split_tensors(5, [], lambda t: True) == 5
+
+
+def test_gpu_compute_without_gpu_falls_back_to_plain_rank_processes_for_python_callables():
+    """kt.Compute(gpus=N).distribute("spmd") with an arbitrary callable is the process route; on a box without
+    CUDA it still runs (tensors travel pickled) — only @mapped/b200 callables require the device library."""
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only behaviour")
+    f = kt.fn(cases.double, name="gpu-less").to(
+        kt.Compute(gpus=2, allowed_serialization=["json", "pickle"]).distribute("spmd", workers=1, num_proc=2))
+    try:
+        x = torch.arange(7, dtype=torch.float32)
+        out = f(x, serialization="pickle")
+        assert torch.equal(torch.cat(out), x * 2)
+    finally:
+        f.teardown()

@@ -13,8 +13,7 @@ import kubetorch_b200 as kt  # noqa: E402
 from oracle import cases, ref_dispatch  # noqa: E402
 
 
-def _mapped(fn, *a, **k):
-    return kt.mapped(*a, **k)(fn)
+from conftest import mapped_copy as _mapped  # noqa: E402
 
 
 @pytest.fixture(scope="module", autouse=True)

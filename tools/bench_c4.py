@@ -11,6 +11,13 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 import torch  # noqa: E402
 
+
+def _clone(fn):
+    """A copy of an oracle callable to decorate (the shared function object stays undecorated)."""
+    import types
+
+    return types.FunctionType(fn.__code__, fn.__globals__, fn.__name__, fn.__defaults__, fn.__closure__)
+
 import kubetorch_b200 as kt  # noqa: E402
 from oracle import cases  # noqa: E402
 
@@ -24,7 +31,7 @@ def main():
     w1 = (torch.randn(1024, 256, device="cuda:0", generator=g) * 0.02).bfloat16()
     w2 = (torch.randn(1024, 1024, device="cuda:0", generator=g) * 0.02).bfloat16()
     w3 = (torch.randn(64, 1024, device="cuda:0", generator=g) * 0.02).bfloat16()
-    policy = kt.mapped("mlp")(cases.mlp_policy)
+    policy = kt.mapped("mlp")(_clone(cases.mlp_policy))
     remote = kt.fn(policy, name="c4-policy").to(kt.Compute(gpus=n_gpus).distribute("b200", workers=1, num_proc=n_gpus))
     for _ in range(3):
         out = remote(obs, w1, w2, w3, serialization="pickle")

@@ -12,6 +12,13 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 import torch  # noqa: E402
 
+
+def _clone(fn):
+    """A copy of an oracle callable to decorate (the shared function object stays undecorated)."""
+    import types
+
+    return types.FunctionType(fn.__code__, fn.__globals__, fn.__name__, fn.__defaults__, fn.__closure__)
+
 import kubetorch_b200 as kt  # noqa: E402
 from kubetorch_b200.device import ops  # noqa: E402
 from oracle import cases  # noqa: E402
@@ -79,7 +86,7 @@ def numa_pinned(n_elems, n_gpus):
 def main():
     n_gpus = int(sys.argv[1]) if len(sys.argv) > 1 else torch.cuda.device_count()
     n = 1 << 26
-    double = kt.mapped("scale", alpha=2.0)(cases.double)
+    double = kt.mapped("scale", alpha=2.0)(_clone(cases.double))
     remote = kt.fn(double, name="host-sweep").to(kt.Compute(gpus=n_gpus).distribute("b200", workers=1, num_proc=n_gpus))
     emit(what="numa", cpus={r: (sorted(gpu_numa_cpus(r))[:2] if gpu_numa_cpus(r) else None) for r in range(n_gpus)})
     for kind in ("plain_pinned", "numa_first_touch_registered"):
