@@ -221,6 +221,14 @@ int ktb_push_status(int dev, const void* ctrl, unsigned int* out);
 int ktb_map_host(int dev, int op, int dtype, const void* src_host, void* dst_host, size_t n_elems,
                  double alpha, double beta, size_t chunk_bytes, void* stage_in, void* stage_out);
 
+/* The same for a sharded call on n_ranks DISTINCT devices, driven from one host thread: rank r's
+ * `x.chunk(n_ranks)[r]` (granule as in ktb_scatter_map_gather) moves host → devs[r] → host over that GPU's
+ * own PCIe link; chunks are issued chunk-major so all links start at once.  stage_in[r] / stage_out[r]
+ * are device buffers of >= 2*chunk_bytes on devs[r].  Synchronous. */
+int ktb_map_host_multi(int op, int dtype, const void* src_host, void* dst_host, size_t n_elems,
+                       size_t granule, double alpha, double beta, int n_ranks, const int* devs,
+                       size_t chunk_bytes, void* const* stage_in, void* const* stage_out);
+
 /* ---- bf16 MLP policy (BASELINE config C4) ---------------------------------------------------------- */
 
 /* logits[M,d_out] = W3·relu(W2·relu(W1·obs^T)) with bf16 storage, fp32 accumulation on tcgen05
@@ -232,6 +240,13 @@ size_t ktb_mlp_scratch_bytes(size_t M, int d_hidden);
 int ktb_mlp_bf16(int dev, const void* obs, size_t M, int d_in, int d_hidden, int d_out,
                  const void* W1, const void* W2, const void* W3, void* logits, void* scratch,
                  uintptr_t stream);
+/* Scatter-fused form for a rank whose observations live on the ROOT GPU: row chunks are pulled
+ * peer → local into `stage` (ktb_mlp_stage_bytes, double-buffered) on a library side stream while
+ * the previous chunk computes; `logits` may be a peer pointer (fused gather). */
+size_t ktb_mlp_stage_bytes(size_t M, int d_in);
+int ktb_mlp_bf16_staged(int dev, const void* obs_peer, size_t M, int d_in, int d_hidden, int d_out,
+                        const void* W1, const void* W2, const void* W3, void* logits, void* scratch,
+                        void* stage, uintptr_t stream);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,7 @@ struct DeviceInfo {
   cudaStream_t stream_h2d = nullptr, stream_exec = nullptr, stream_d2h = nullptr;  // ktb_map_host
   cudaStream_t stream_rank = nullptr;                                              // multi-GPU default
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  cudaEvent_t host_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // ktb_map_host_multi
 };
 constexpr int kMaxDevices = 16;
 DeviceInfo* device_info(int dev);   // nullptr when unregistered

@@ -29,8 +29,8 @@ constexpr int kMlpBlockM = 128;
 constexpr int kMlpBlockK = 64;   // 64 bf16 = 128 bytes = one SWIZZLE_128B row
 constexpr int kMlpUmmaK = 16;
 constexpr int kMlpThreads = 192;
-constexpr size_t kMlpChunkRows = 16384;
-int g_mlp_persistent = 1;  // ktb_set_tuning key 7: 1 = persistent double-buffered kernel, 0 = one tile per CTA  // 2 x 32 MiB of hidden activations per chunk (d_hidden = 1024)
+int g_mlp_chunk_rows = 16384;  // ktb_set_tuning key 8: rows per chunk (2 x 32 MiB of hidden activations at d_hidden = 1024)
+int g_mlp_persistent = 1;      // ktb_set_tuning key 7: 1 = persistent double-buffered kernel, 0 = one tile per CTA
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -416,12 +416,17 @@ using namespace ktb;
 extern "C" {
 
 size_t ktb_mlp_scratch_bytes(size_t M, int d_hidden) {
-  const size_t rows = std::min<size_t>(M, kMlpChunkRows);
+  const size_t rows = std::min<size_t>(M, (size_t)g_mlp_chunk_rows);
   return 2 * rows * (size_t)d_hidden * 2;
 }
 
-int ktb_mlp_bf16(int dev, const void* obs, size_t M, int d_in, int d_hidden, int d_out, const void* W1,
-                 const void* W2, const void* W3, void* logits, void* scratch, uintptr_t stream) {
+size_t ktb_mlp_stage_bytes(size_t M, int d_in) {
+  const size_t rows = std::min<size_t>(M, (size_t)g_mlp_chunk_rows);
+  return 2 * rows * (size_t)d_in * 2;
+}
+
+static int mlp_run(int dev, const void* obs, size_t M, int d_in, int d_hidden, int d_out, const void* W1,
+                   const void* W2, const void* W3, void* logits, void* scratch, void* stage, uintptr_t stream) {
   int rc = require_device(dev);
   if (rc) return rc;
   if (M == 0) return KTB_OK;
@@ -432,27 +437,62 @@ int ktb_mlp_bf16(int dev, const void* obs, size_t M, int d_in, int d_hidden, int
               d_hidden);
   KTB_REQUIRE(d_out == 64, KTB_ERR_UNSUPPORTED, "ktb_mlp_bf16: d_out=%d (this build carries the 64-wide head)", d_out);
   KTB_REQUIRE((((uintptr_t)obs | (uintptr_t)W1 | (uintptr_t)W2 | (uintptr_t)W3 | (uintptr_t)logits |
-                (uintptr_t)scratch) & 15) == 0,
+                (uintptr_t)scratch | (uintptr_t)stage) & 15) == 0,
               KTB_ERR_ARG, "ktb_mlp_bf16: all pointers must be 16-byte aligned");
+  KTB_REQUIRE(g_mlp_chunk_rows % kMlpBlockM == 0 && g_mlp_chunk_rows > 0, KTB_ERR_ARG, "ktb_mlp_bf16: bad chunk rows");
   rc = get_encoder();
   if (rc) return rc;
   KTB_GUARD(dev);
+  DeviceInfo* di = device_info(dev);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const size_t chunk = std::min<size_t>(M, kMlpChunkRows);
+  cudaStream_t side = di->stream_exec;   // pulls the next chunk while this one computes
+  const size_t chunk = std::min<size_t>(M, (size_t)g_mlp_chunk_rows);
   __nv_bfloat16* h1 = static_cast<__nv_bfloat16*>(scratch);
   __nv_bfloat16* h2 = h1 + chunk * (size_t)d_hidden;
   const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(obs);
   __nv_bfloat16* y = static_cast<__nv_bfloat16*>(logits);
-  for (size_t r0 = 0; r0 < M; r0 += chunk) {
+  __nv_bfloat16* stg = static_cast<__nv_bfloat16*>(stage);
+  const MapParams ident = make_params(1, 0);
+  if (stg) {
+    KTB_CK(cudaEventRecord(di->ev_a, st));          // obs is ready once prior work on `st` is done
+    KTB_CK(cudaStreamWaitEvent(side, di->ev_a, 0));
+  }
+  size_t c = 0;
+  for (size_t r0 = 0; r0 < M; r0 += chunk, ++c) {
     const size_t rows = std::min(chunk, M - r0);
-    rc = launch_gemm<256, 4, true>(x + r0 * d_in, W1, h1, rows, d_hidden, d_in, d_hidden, st);
+    const __nv_bfloat16* a1 = x + r0 * d_in;
+    if (stg) {
+      // staged pull: rows of this chunk travel peer → local ONCE (the layer-1 GEMM would otherwise fetch every
+      // A tile d_hidden/256 times over NVLink, peer reads being uncached in the local L2)
+      const int b = (int)(c & 1);
+      __nv_bfloat16* dstb = stg + (size_t)b * chunk * d_in;
+      if (c >= 2) KTB_CK(cudaStreamWaitEvent(side, di->host_ev[2 + b], 0));   // GEMM 1 of chunk c-2 consumed it
+      rc = launch_map(dev, KTB_OP_IDENTITY, KTB_U8, a1, dstb, rows * (size_t)d_in * 2, ident, KTB_VARIANT_AUTO, side);
+      if (rc) return rc;
+      KTB_CK(cudaEventRecord(di->host_ev[b], side));
+      KTB_CK(cudaStreamWaitEvent(st, di->host_ev[b], 0));
+      a1 = dstb;
+    }
+    rc = launch_gemm<256, 4, true>(a1, W1, h1, rows, d_hidden, d_in, d_hidden, st);
     if (rc) return rc;
+    if (stg) KTB_CK(cudaEventRecord(di->host_ev[2 + (int)(c & 1)], st));
     rc = launch_gemm<256, 4, true>(h1, W2, h2, rows, d_hidden, d_hidden, d_hidden, st);
     if (rc) return rc;
     rc = launch_gemm<64, 4, false>(h2, W3, y + r0 * d_out, rows, d_out, d_hidden, d_out, st);
     if (rc) return rc;
   }
   return KTB_OK;
+}
+
+int ktb_mlp_bf16(int dev, const void* obs, size_t M, int d_in, int d_hidden, int d_out, const void* W1,
+                 const void* W2, const void* W3, void* logits, void* scratch, uintptr_t stream) {
+  return mlp_run(dev, obs, M, d_in, d_hidden, d_out, W1, W2, W3, logits, scratch, nullptr, stream);
+}
+
+int ktb_mlp_bf16_staged(int dev, const void* obs_peer, size_t M, int d_in, int d_hidden, int d_out, const void* W1,
+                        const void* W2, const void* W3, void* logits, void* scratch, void* stage, uintptr_t stream) {
+  KTB_REQUIRE(stage, KTB_ERR_ARG, "ktb_mlp_bf16_staged: null stage buffer");
+  return mlp_run(dev, obs_peer, M, d_in, d_hidden, d_out, W1, W2, W3, logits, scratch, stage, stream);
 }
 
 }  // extern "C"

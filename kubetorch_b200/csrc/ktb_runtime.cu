@@ -56,6 +56,7 @@ static int register_device(int dev) {
   KTB_CK(cudaStreamCreateWithFlags(&d.stream_rank, cudaStreamNonBlocking));
   KTB_CK(cudaEventCreateWithFlags(&d.ev_a, cudaEventDisableTiming));
   KTB_CK(cudaEventCreateWithFlags(&d.ev_b, cudaEventDisableTiming));
+  for (int i = 0; i < 6; ++i) KTB_CK(cudaEventCreateWithFlags(&d.host_ev[i], cudaEventDisableTiming));
   d.registered = true;
   g_peer[dev][dev] = true;
   return KTB_OK;
@@ -124,6 +125,7 @@ int ktb_shutdown(void) {
     cudaStreamDestroy(g_dev[d].stream_rank);
     cudaEventDestroy(g_dev[d].ev_a);
     cudaEventDestroy(g_dev[d].ev_b);
+    for (int i = 0; i < 6; ++i) cudaEventDestroy(g_dev[d].host_ev[i]);
     g_dev[d] = DeviceInfo();
   }
   for (auto& kv : g_host) cudaFreeHost(kv.first);

@@ -75,8 +75,13 @@ _SIGNATURES = {
     "ktb_push_wait": (c_int, [c_int, c_void_p, c_int, c_int, ctypes.c_ulonglong, c_uintptr]),
     "ktb_push_status": (c_int, [c_int, c_void_p, POINTER(ctypes.c_uint)]),
     "ktb_map_host": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_double, c_double, c_size_t, c_void_p, c_void_p]),
+    "ktb_map_host_multi": (c_int, [c_int, c_int, c_void_p, c_void_p, c_size_t, c_size_t, c_double, c_double, c_int,
+                                   POINTER(c_int), c_size_t, POINTER(c_void_p), POINTER(c_void_p)]),
     "ktb_mlp_scratch_bytes": (c_size_t, [c_size_t, c_int]),
     "ktb_mlp_bf16": (c_int, [c_int, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uintptr]),
+    "ktb_mlp_stage_bytes": (c_size_t, [c_size_t, c_int]),
+    "ktb_mlp_bf16_staged": (c_int, [c_int, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_uintptr]),
     # experiment knob, not in the stable header
     "ktb_set_tuning": (c_int, [c_int, c_int]),
 }

@@ -11,7 +11,9 @@ from . import lib as L
 from . import ops
 
 _scratch = {}
+_stage = {}
 _weight_cache = {}
+_pool = None
 
 
 def _scratch_for(dev: int, M: int, d_hidden: int) -> torch.Tensor:
@@ -23,9 +25,18 @@ def _scratch_for(dev: int, M: int, d_hidden: int) -> torch.Tensor:
     return buf
 
 
+def _stage_for(dev: int, M: int, d_in: int) -> torch.Tensor:
+    nbytes = L.load().ktb_mlp_stage_bytes(M, d_in)
+    buf = _stage.get(dev)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{dev}")
+        _stage[dev] = buf
+    return buf
+
+
 def mlp_forward(obs: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor, w3: torch.Tensor,
                 out: Optional[torch.Tensor] = None, device: Optional[int] = None,
-                stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+                stream: Optional[torch.cuda.Stream] = None, staged: Optional[bool] = None) -> torch.Tensor:
     """logits[M, d_out] = W3·relu(W2·relu(W1·obsᵀ)); bf16 storage, fp32 accumulation in TMEM.
     `obs` / `out` may be peer-mapped (pull the observations / push the logits over NVLink)."""
     for name, t in (("obs", obs), ("w1", w1), ("w2", w2), ("w3", w3)):
@@ -42,8 +53,15 @@ def mlp_forward(obs: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor, w3: torch
     else:
         ops.ensure_init({out.device.index})
     s = stream if stream is not None else torch.cuda.current_stream(dev)
-    L.call("ktb_mlp_bf16", dev, obs.data_ptr(), M, d_in, d_hidden, d_out, w1.data_ptr(), w2.data_ptr(), w3.data_ptr(),
-           out.data_ptr(), _scratch_for(dev, M, d_hidden).data_ptr(), int(s.cuda_stream))
+    if staged is None:
+        staged = obs.device.index != dev   # observations on another GPU: pull each row chunk over NVLink once
+    if staged:
+        L.call("ktb_mlp_bf16_staged", dev, obs.data_ptr(), M, d_in, d_hidden, d_out, w1.data_ptr(), w2.data_ptr(),
+               w3.data_ptr(), out.data_ptr(), _scratch_for(dev, M, d_hidden).data_ptr(),
+               _stage_for(dev, M, d_in).data_ptr(), int(s.cuda_stream))
+    else:
+        L.call("ktb_mlp_bf16", dev, obs.data_ptr(), M, d_in, d_hidden, d_out, w1.data_ptr(), w2.data_ptr(),
+               w3.data_ptr(), out.data_ptr(), _scratch_for(dev, M, d_hidden).data_ptr(), int(s.cuda_stream))
     return out
 
 
@@ -83,22 +101,43 @@ def mlp_scatter_gather(obs_root: torch.Tensor, w1, w2, w3, devices: Sequence[int
     root_stream = torch.cuda.current_stream(root)
     ready = torch.cuda.Event()
     ready.record(root_stream)
-    views, done = [], []
-    for r, dev in enumerate(devs):
-        b, e = ops.shard_bounds(M, len(devs), r)
-        views.append(out_root[b:e])
+    bounds = [ops.shard_bounds(M, len(devs), r) for r in range(len(devs))]
+    views = [out_root[b:e] for b, e in bounds]
+    weights = {dev: _weights_on(dev, (w1, w2, w3)) for dev in set(devs)}
+    for dev in set(devs):       # allocate scratch/staging on the calling thread (allocator + first use)
+        _scratch_for(dev, max(e - b for b, e in bounds), w1.shape[0])
+        if dev != root:
+            _stage_for(dev, max(e - b for b, e in bounds), obs_root.shape[1])
+    streams = {dev: torch.cuda.current_stream(dev) for dev in set(devs)}
+
+    def issue(r):
+        """Enqueue rank r's whole pipeline (≈50 launches); ctypes releases the GIL, so ranks issue in parallel."""
+        dev = devs[r]
+        b, e = bounds[r]
         if e == b:
-            continue
-        ws = _weights_on(dev, (w1, w2, w3))
+            return None
+        ws = weights[dev]
+        st = streams[dev]
         with torch.cuda.device(dev):
-            st = torch.cuda.current_stream(dev)
             if dev != root:
                 st.wait_event(ready)
             mlp_forward(obs_root[b:e], ws[0], ws[1], ws[2], out=out_root[b:e], device=dev, stream=st)
             if dev != root:
                 ev = torch.cuda.Event()
                 ev.record(st)
-                done.append(ev)
+                return ev
+        return None
+
+    global _pool
+    if len(set(devs)) > 1:
+        if _pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+
+            _pool = ThreadPoolExecutor(max_workers=16, thread_name_prefix="ktb-mlp")
+        done = list(_pool.map(issue, range(len(devs))))
+    else:
+        done = [issue(r) for r in range(len(devs))]
     for ev in done:
-        root_stream.wait_event(ev)
+        if ev is not None:
+            root_stream.wait_event(ev)
     return views

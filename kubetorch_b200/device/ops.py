@@ -522,5 +522,55 @@ def map_host(
     return out_host
 
 
+_multi_lock = threading.Lock()
+
+
+def host_chunk_bytes(shard_bytes: int) -> int:
+    """Chunk size of the host pipeline: ~4 chunks per shard, between 1 MiB and 16 MiB, 256-byte multiple."""
+    c = max(1 << 20, min(16 << 20, shard_bytes // 4))
+    return (c + 255) // 256 * 256
+
+
+def map_host_multi(
+    x_host: torch.Tensor,
+    op: str,
+    alpha: float = 1.0,
+    beta: float = 0.0,
+    out_host: Optional[torch.Tensor] = None,
+    devices: Sequence[int] = (0,),
+    chunk_bytes: Optional[int] = None,
+) -> torch.Tensor:
+    """Sharded host-resident call on distinct GPUs from ONE host thread (ktb_map_host_multi)."""
+    require_cuda()
+    if x_host.is_cuda or not x_host.is_pinned():
+        raise ValueError("x_host must be a pinned host tensor")
+    if out_host is None:
+        out_host = torch.empty_like(x_host).pin_memory()
+    devs = [int(d) for d in devices]
+    ensure_init(set(devs))
+    gran = row_elems(x_host)
+    rows = x_host.numel() // gran
+    shard_bytes = shard_bounds(rows, len(devs), 0)[1] * gran * x_host.element_size()
+    cb = int(chunk_bytes or host_chunk_bytes(shard_bytes))
+    with _multi_lock:
+        stages = []
+        for d in devs:
+            key = (d, cb)
+            st = _stage_cache.get(key)
+            if st is None:
+                st = (torch.empty(2 * cb, dtype=torch.uint8, device=f"cuda:{d}"),
+                      torch.empty(2 * cb, dtype=torch.uint8, device=f"cuda:{d}"))
+                torch.cuda.synchronize(d)
+                _stage_cache[key] = st
+            stages.append(st)
+        L.call(
+            "ktb_map_host_multi", OPS[op], dtype_code(x_host.dtype), x_host.data_ptr(), out_host.data_ptr(),
+            x_host.numel(), gran, float(alpha), float(beta), len(devs), L.arr(ctypes.c_int, devs), cb,
+            L.arr(ctypes.c_void_p, [s[0].data_ptr() for s in stages]),
+            L.arr(ctypes.c_void_p, [s[1].data_ptr() for s in stages]),
+        )
+    return out_host
+
+
 def set_tuning(key: int, value: int) -> None:
     L.call("ktb_set_tuning", key, value)

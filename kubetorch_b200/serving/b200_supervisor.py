@@ -185,6 +185,10 @@ class B200Supervisor:
         out = self._pinned("out", x)
         x_shards = self._shard_views(x, x)
         o_shards = self._shard_views(out, x)
+        if len(set(self.devices)) == len(self.devices):
+            # one C call drives every GPU's copy/exec/copy pipeline (no per-rank Python threads)
+            ops.map_host_multi(x, op, alpha, beta, out_host=out, devices=self.devices)
+            return o_shards
 
         def run(rank):
             if x_shards[rank].numel():

@@ -147,6 +147,17 @@ def test_two_gpu_peer_path_matches_oracle():
     xi = torch.randint(-(2**40), 2**40, (100_003,), dtype=torch.int64)
     total, partials = ops.scatter_map_reduce(xi.cuda(0), "identity", devices=[0, 1])
     assert partials.tolist() == ref_dispatch.spmd_call(cases.shard_sum, xi, num_proc=2, serialization="pickle")
+    xh = torch.randn((1 << 21) + 3).pin_memory()   # host-resident, both GPUs from one host thread
+    assert torch.equal(ops.map_host_multi(xh, "scale", 2.0, devices=[0, 1]), xh * 2.0)
+    from kubetorch_b200.device import mlp
+
+    g = torch.Generator().manual_seed(3)
+    obs = torch.randn(1024, 256, generator=g).bfloat16().cuda(0)
+    w = [(torch.randn(s, generator=g) * 0.02).bfloat16().cuda(0) for s in ((1024, 256), (1024, 1024), (64, 1024))]
+    single = mlp.mlp_forward(obs, *w)
+    views = mlp.mlp_scatter_gather(obs, *w, devices=[0, 1])   # rank 1: staged NVLink pull + peer-store epilogue
+    torch.cuda.synchronize(0)
+    assert torch.equal(torch.cat(views).cpu(), single.cpu())
     dst = torch.empty(1 << 20, dtype=torch.uint8, device="cuda:1")
     src = torch.randint(0, 255, (1 << 20,), dtype=torch.uint8, device="cuda:0")
     ops.broadcast(src, [dst])

@@ -223,6 +223,15 @@ def test_map_host_pipeline(K):
         assert torch.equal(out, x * 0.25 + -1.0)
 
 
+def test_map_host_multi_single_thread_pipeline(K):
+    for n in [3, 70_001, (1 << 22) + 5]:
+        x = _rand(torch.float32, n, seed=9).pin_memory()
+        out = K.map_host_multi(x, "affine", 1.5, 0.5, devices=[0], chunk_bytes=1 << 20)
+        assert torch.equal(out, x * 1.5 + 0.5)
+    x2 = _rand(torch.int32, 40_000).reshape(100, 400).pin_memory()
+    assert torch.equal(K.map_host_multi(x2, "scale", 3, devices=[0]), x2 * 3)
+
+
 def test_zero_copy_host_pointers(K):
     """Mapped pinned host memory is a valid src/dst for the kernels (UVA)."""
     x = _rand(torch.float32, 100_000).pin_memory()
@@ -278,6 +287,11 @@ def test_mlp_tcgen05_matches_recorded_reference_and_fp32(K, golden):
     got2 = mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float()
     want2 = _mlp_ref(obs2, inp["mlp_w1"], inp["mlp_w2"], inp["mlp_w3"]).float()
     torch.testing.assert_close(got2, want2, rtol=2**-7, atol=1e-2)
+    # staged form (row chunks pulled through a double-buffered staging area on a side stream): identical bits
+    K.set_tuning(8, 4096)  # several chunks
+    got3 = mlp.mlp_forward(obs2.cuda(), w1, w2, w3, staged=True).cpu().float()
+    K.set_tuning(8, 16384)
+    assert torch.equal(got3, got2)
     # top-1 action agrees wherever the fp32 top-2 logit gap exceeds 2^-6
     top2 = want2.topk(2, dim=1).values
     clear = (top2[:, 0] - top2[:, 1]) > 2**-6
