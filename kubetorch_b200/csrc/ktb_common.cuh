@@ -46,7 +46,9 @@ struct DeviceGuard {
   cudaError_t err = cudaSuccess;
   explicit DeviceGuard(int dev) {
     err = cudaGetDevice(&prev);
-    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    // always bind: on a fresh host thread cudaGetDevice reports 0 without making a context current, and
+    // driver entry points (cuTensorMapEncodeTiled) need a current context
+    if (err == cudaSuccess) err = cudaSetDevice(dev);
     ok = (err == cudaSuccess);
   }
   ~DeviceGuard() {

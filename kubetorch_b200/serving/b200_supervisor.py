@@ -32,7 +32,7 @@ class B200Supervisor:
     def __init__(self, pointers=None, init_args=None, name: str = None, devices: Optional[List[int]] = None,
                  num_proc=None, distributed: bool = True, allowed_serialization: str = "json,pickle",
                  host_chunk_bytes: int = 16 << 20, variant: int = 0, callable_obj=None, transfer: str = "auto",
-                 **extra):
+                 host_mode: str = "multi", **extra):
         self.pointers, self.init_args, self.name = pointers, init_args, name
         self.callable_obj = callable_obj
         self.devices = list(devices) if devices is not None else None
@@ -50,6 +50,7 @@ class B200Supervisor:
         if transfer not in ("auto", "pull", "push"):
             raise ValueError("transfer must be 'auto', 'pull' or 'push'")
         self.transfer = transfer
+        self.host_mode = host_mode  # "multi": one C call drives all GPUs; "threads": one host thread per rank
         self.config_hash = hash(("b200", tuple(self.devices or ()), num_proc, distributed))
 
     # ---- lifecycle ------------------------------------------------------------------------------------
@@ -185,7 +186,7 @@ class B200Supervisor:
         out = self._pinned("out", x)
         x_shards = self._shard_views(x, x)
         o_shards = self._shard_views(out, x)
-        if len(set(self.devices)) == len(self.devices):
+        if self.host_mode == "multi" and len(set(self.devices)) == len(self.devices):
             # one C call drives every GPU's copy/exec/copy pipeline (no per-rank Python threads)
             ops.map_host_multi(x, op, alpha, beta, out_host=out, devices=self.devices)
             return o_shards

@@ -87,20 +87,35 @@ def main():
     n_gpus = int(sys.argv[1]) if len(sys.argv) > 1 else torch.cuda.device_count()
     n = 1 << 26
     double = kt.mapped("scale", alpha=2.0)(_clone(cases.double))
-    remote = kt.fn(double, name="host-sweep").to(kt.Compute(gpus=n_gpus).distribute("b200", workers=1, num_proc=n_gpus))
     emit(what="numa", cpus={r: (sorted(gpu_numa_cpus(r))[:2] if gpu_numa_cpus(r) else None) for r in range(n_gpus)})
-    for kind in ("plain_pinned", "numa_first_touch_registered"):
-        xh = torch.randn(n).pin_memory() if kind == "plain_pinned" else numa_pinned(n, n_gpus)
-        assert xh.is_pinned()
-        for _ in range(2):
-            out = remote(xh, serialization="pickle")
+    bufs = {"plain_pinned": torch.randn(n).pin_memory(), "numa_first_touch_registered": numa_pinned(n, n_gpus)}
+    for host_mode in ("threads", "multi"):
+        remote = kt.fn(double, name=f"host-sweep-{host_mode}").to(
+            kt.Compute(gpus=n_gpus).distribute("b200", workers=1, num_proc=n_gpus, host_mode=host_mode))
+        for kind, xh in bufs.items():
+            assert xh.is_pinned()
+            for _ in range(2):
+                out = remote(xh, serialization="pickle")
+            t0 = time.perf_counter()
+            for _ in range(8):
+                out = remote(xh, serialization="pickle")
+            dt = (time.perf_counter() - t0) / 8
+            ok = bool(torch.equal(torch.cat(out)[-4096:], xh[-4096:] * 2))
+            emit(what="e2e_host", host_mode=host_mode, kind=kind, n_gpus=n_gpus, ms=dt * 1e3,
+                 gbps=2 * n * 4 / dt / 1e9, ok=ok)
+        remote.teardown()
+    # raw pipeline without the API layer, by chunk size
+    from kubetorch_b200.device import ops as _ops
+
+    xh = bufs["plain_pinned"]
+    yh = torch.empty_like(xh).pin_memory()
+    for cb in (2 << 20, 4 << 20, 8 << 20, 16 << 20):
+        _ops.map_host_multi(xh, "scale", 2.0, out_host=yh, devices=list(range(n_gpus)), chunk_bytes=cb)
         t0 = time.perf_counter()
-        for _ in range(8):
-            out = remote(xh, serialization="pickle")
-        dt = (time.perf_counter() - t0) / 8
-        ok = bool(torch.equal(torch.cat(out)[-4096:], xh[-4096:] * 2))
-        emit(what="e2e_host", kind=kind, n_gpus=n_gpus, ms=dt * 1e3, gbps=2 * n * 4 / dt / 1e9, ok=ok)
-    remote.teardown()
+        for _ in range(5):
+            _ops.map_host_multi(xh, "scale", 2.0, out_host=yh, devices=list(range(n_gpus)), chunk_bytes=cb)
+        dt = (time.perf_counter() - t0) / 5
+        emit(what="map_host_multi_raw", n_gpus=n_gpus, chunk_bytes=cb, ms=dt * 1e3, gbps=2 * n * 4 / dt / 1e9)
 
 
 if __name__ == "__main__":
