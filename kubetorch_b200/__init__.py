@@ -4,6 +4,7 @@ that path: kt.Compute / kt.fn / kt.cls / .to() / .distribute() / remote __call__
 (exports mirror kt/__init__.py:1-36), with `kt.Compute(gpus=N)` bound to N local B200s.
 """
 from . import distributed  # noqa: F401
+from .data_store import BroadcastWindow, get, ls, put, rm  # noqa: F401
 from .config import DebugConfig, LoggingConfig, MetricsConfig, config  # noqa: F401
 from .exceptions import (  # noqa: F401
     EXCEPTION_REGISTRY,

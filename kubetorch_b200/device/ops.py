@@ -279,11 +279,13 @@ def map_batch(
     beta: float = 0.0,
     outs: Optional[Sequence[torch.Tensor]] = None,
     stream: Optional[torch.cuda.Stream] = None,
+    device: Optional[int] = None,
 ) -> Sequence[torch.Tensor]:
-    """n independent small calls out_i = op(x_i) coalesced into one segmented launch."""
+    """n independent small calls out_i = op(x_i) coalesced into one segmented launch (on `device`,
+    default xs[0]'s; sources/destinations may be peer-mapped)."""
     if not xs:
         return []
-    dev = _check_dev_tensor(xs[0], "xs[0]")
+    dev = _check_dev_tensor(xs[0], "xs[0]") if device is None else int(device)
     ensure_init({dev})
     dt = xs[0].dtype
     for i, t in enumerate(xs):

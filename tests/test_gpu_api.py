@@ -197,3 +197,56 @@ def test_arbitrary_callables_on_gpu_ranks_use_hbm_arenas(golden):
         assert float(out[0]["sum"]) == 132.0 and out[1]["y"].tolist() == [11, 21] and out[1]["y"].is_cuda
     finally:
         mixed.teardown()
+
+
+def test_kt_put_get_gpu_store_patterns():
+    """kt.put / kt.get of GPU tensors and state dicts with the reference's test patterns:
+    torch.full fills, several dtypes, state dicts, packed BroadcastWindow (tests/assets/kv_store/gpu_helper.py)."""
+    import threading
+
+    n_dev = torch.cuda.device_count()
+    dst_dev = f"cuda:{1 if n_dev > 1 else 0}"
+    for dtype, fill in ((torch.float32, 3.5), (torch.bfloat16, -2.0), (torch.int64, 7), (torch.uint8, 200)):
+        src = torch.full((257, 33), fill, dtype=dtype, device="cuda:0")
+        kt.put(key=f"t/{dtype}", src=src)
+        dest = torch.zeros_like(src, device=dst_dev)
+        kt.get(key=f"t/{dtype}", dest=dest)
+        torch.cuda.synchronize()
+        assert torch.equal(dest.cpu(), src.cpu())
+    sd = {"layer1": {"weight": torch.randn(64, 32, device="cuda:0"), "bias": torch.randn(64, device="cuda:0")},
+          "head.weight": torch.randn(10, 64, device="cuda:0").bfloat16(), "step": torch.tensor(5, device="cuda:0")}
+    kt.put(key="model/weights", src=sd)
+    assert kt.ls("model/weights") == ["model/weights/head.weight", "model/weights/layer1.bias",
+                                      "model/weights/layer1.weight", "model/weights/step"]
+    dest_sd = {"layer1": {"weight": torch.zeros(64, 32, device=dst_dev), "bias": torch.zeros(64, device=dst_dev)},
+               "head.weight": torch.zeros(10, 64, device=dst_dev).bfloat16(), "step": torch.tensor(0, device=dst_dev)}
+    kt.get(key="model/weights", dest=dest_sd)
+    one = torch.zeros(64, device=dst_dev)
+    kt.get(key="model/weights/layer1.bias", dest=one)   # a single leaf of a published state dict
+    torch.cuda.synchronize()
+    assert torch.equal(dest_sd["layer1"]["weight"].cpu(), sd["layer1"]["weight"].cpu())
+    assert torch.equal(dest_sd["head.weight"].cpu(), sd["head.weight"].cpu()) and int(dest_sd["step"]) == 5
+    assert torch.equal(one.cpu(), sd["layer1"]["bias"].cpu())
+    # packed broadcast: 1 putter + 2 getters, one read of the source, unpack on arrival
+    bw = kt.BroadcastWindow(world_size=3, timeout=30.0, group_id="g1", pack=True)
+    dests = [{k: torch.zeros_like(v, device=dst_dev if i else "cuda:0") for k, v in
+              {"a": sd["layer1"]["weight"], "b": sd["layer1"]["bias"]}.items()} for i in range(2)]
+    results = []
+    ths = [threading.Thread(target=lambda d=d: results.append(kt.get(key="bc", dest=d, broadcast=bw))) for d in dests]
+    [t.start() for t in ths]
+    r = kt.put(key="bc", src={"a": sd["layer1"]["weight"], "b": sd["layer1"]["bias"]}, broadcast=bw)
+    [t.join() for t in ths]
+    torch.cuda.synchronize()
+    assert r["world_size"] == 3 and len(results) == 2
+    for d in dests:
+        assert torch.equal(d["a"].cpu(), sd["layer1"]["weight"].cpu()) and torch.equal(d["b"].cpu(), sd["layer1"]["bias"].cpu())
+    with pytest.raises(kt.DataStoreError, match="not found"):
+        kt.get(key="nope", dest=torch.zeros(1, device="cuda:0"))
+    with pytest.raises(ValueError, match="stored tensor"):
+        kt.get(key="model/weights/layer1.bias", dest=torch.zeros(65, device="cuda:0"))
+    with pytest.raises(ValueError, match="must be on a CUDA device"):
+        kt.put(key="cpu", src={"w": torch.zeros(2), "g": torch.zeros(2, device="cuda:0")})
+    kt.rm("model/weights")
+    assert kt.ls("model/weights") == []
+    with pytest.raises(kt.DataStoreError, match="timed out"):
+        kt.get(key="late", dest=torch.zeros(1, device="cuda:0"), broadcast=kt.BroadcastWindow(world_size=2, timeout=0.3))
