@@ -76,6 +76,15 @@ def row_elems(t: torch.Tensor) -> int:
 
 
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Python twin of ktb_shard_bounds (tests/test_abi.py checks they agree): `x.chunk(world)[rank]` bounds."""
+    if world <= 0 or rank < 0 or rank >= world:
+        raise ValueError(f"bad world/rank {world}/{rank}")
+    chunk = -(-n // world)
+    b = min(n, chunk * rank)
+    return b, min(n, b + chunk)
+
+
+def shard_bounds_c(n: int, world: int, rank: int) -> Tuple[int, int]:
     b, e = ctypes.c_size_t(), ctypes.c_size_t()
     L.call("ktb_shard_bounds", n, world, rank, ctypes.byref(b), ctypes.byref(e))
     return b.value, e.value

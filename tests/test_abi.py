@@ -42,6 +42,9 @@ def test_shard_bounds_equal_torch_chunk(n, world):
     for r in range(world):
         b, e = ctypes.c_size_t(), ctypes.c_size_t()
         L.call("ktb_shard_bounds", n, world, r, ctypes.byref(b), ctypes.byref(e))
+        from kubetorch_b200.device import ops
+
+        assert ops.shard_bounds(n, world, r) == (b.value, e.value)   # the Python twin agrees with the C entry
         want = chunks[r] if r < len(chunks) else x[:0]
         assert e.value - b.value == want.numel()
         if want.numel():

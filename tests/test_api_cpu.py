@@ -257,3 +257,18 @@ def test_gpu_compute_without_gpu_falls_back_to_plain_rank_processes_for_python_c
         assert torch.equal(torch.cat(out), x * 2)
     finally:
         f.teardown()
+
+
+def test_data_store_surface_without_gpu():
+    assert kt.BroadcastWindow(world_size=4, pack=True).to_dict()["pack"] is True
+    with pytest.raises(ValueError, match="at least one of"):
+        kt.BroadcastWindow()
+    with pytest.raises(ValueError, match="src is required"):
+        kt.put("k")
+    with pytest.raises(NotImplementedError):
+        kt.put("k", src="./some/dir")          # filesystem keys belong to the Kubernetes rsync store
+    with pytest.raises(NotImplementedError):
+        kt.get("k", dest="./some/dir")
+    with pytest.raises(kt.DataStoreError):
+        kt.rm("never-put")
+    assert kt.ls("never-put") == []
