@@ -29,7 +29,8 @@ constexpr int kMlpBlockM = 128;
 constexpr int kMlpBlockK = 64;   // 64 bf16 = 128 bytes = one SWIZZLE_128B row
 constexpr int kMlpUmmaK = 16;
 constexpr int kMlpThreads = 192;
-int g_mlp_chunk_rows = 16384;  // ktb_set_tuning key 8: rows per chunk (2 x 32 MiB of hidden activations at d_hidden = 1024)
+int g_mlp_chunk_rows = 32768;  // ktb_set_tuning key 8: rows per chunk (2 x 64 MiB of hidden activations at d_hidden = 1024; measured best)
+int g_mlp_epi_groups = 2;      // ktb_set_tuning key 9: epilogue warpgroups (1 or 2) of the persistent kernel
 int g_mlp_persistent = 1;      // ktb_set_tuning key 7: 1 = persistent double-buffered kernel, 0 = one tile per CTA
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
@@ -227,8 +228,8 @@ __global__ void __launch_bounds__(kMlpThreads)
 // epilogue of tile t (tcgen05.ld → ReLU → bf16 → global) overlaps the TMA/MMA main loop of tile t+1.
 //   tmem_full[a]  : MMA warp → epilogue   (tcgen05.commit, count 1)
 //   tmem_empty[a] : epilogue → MMA warp   (one arrive per epilogue warp, count 4)
-template <int BLOCK_N, int STAGES, bool RELU>
-__global__ void __launch_bounds__(kMlpThreads)
+template <int BLOCK_N, int STAGES, bool RELU, int EPI_GROUPS>
+__global__ void __launch_bounds__(64 + 128 * EPI_GROUPS)
     gemm_bf16_tn_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                    __nv_bfloat16* __restrict__ C, int ldc, int K, int tiles_m, int tiles_n) {
   using S = MlpSmem<BLOCK_N, STAGES>;
@@ -255,8 +256,8 @@ __global__ void __launch_bounds__(kMlpThreads)
     }
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], 4);
-    mbar_init(&tmem_empty[1], 4);
+    mbar_init(&tmem_empty[0], 4 * EPI_GROUPS);
+    mbar_init(&tmem_empty[1], 4 * EPI_GROUPS);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_holder, 2 * BLOCK_N);
@@ -306,7 +307,11 @@ __global__ void __launch_bounds__(kMlpThreads)
       }
     }
   } else {
+    // EPI_GROUPS warpgroups of 4 warps: warp w reads TMEM lanes 32*(w%4)..+31; group g takes the g-th slice
+    // of the tile's columns, so two groups halve the epilogue time of a tile
     const int quarter = warp & 3;
+    const int group = (warp - 2) >> 2;
+    constexpr int kColsPerGroup = BLOCK_N / EPI_GROUPS;
     int t = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const int as = t & 1;
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(kMlpThreads)
       tc_fence_after();
       __nv_bfloat16* crow = C + (size_t)(m0 + quarter * 32 + lane) * ldc + n0;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
+      for (int c = group * kColsPerGroup; c < (group + 1) * kColsPerGroup; c += 32) {
         uint32_t acc[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c), acc);
         uint32_t packed[16];
@@ -391,14 +396,20 @@ static int launch_gemm(const void* A, const void* B, void* C, size_t M, int N, i
   rc = make_map(&mb, B, (uint64_t)N, (uint64_t)K, BLOCK_N);
   if (rc) return rc;
   if (g_mlp_persistent) {
-    auto kfn = gemm_bf16_tn_persistent_kernel<BLOCK_N, STAGES, RELU>;
-    KTB_CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     const int tiles_m = (int)(M / kMlpBlockM), tiles_n = N / BLOCK_N;
     int dev = 0;
     KTB_CK(cudaGetDevice(&dev));
     const int sms = device_info(dev) ? device_info(dev)->sm_count : 148;
     const int grid = std::min(tiles_m * tiles_n, sms);
-    kfn<<<grid, kMlpThreads, S::kTotal, stream>>>(ma, mb, static_cast<__nv_bfloat16*>(C), ldc, K, tiles_m, tiles_n);
+    if (g_mlp_epi_groups == 2) {
+      auto kfn = gemm_bf16_tn_persistent_kernel<BLOCK_N, STAGES, RELU, 2>;
+      KTB_CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+      kfn<<<grid, 64 + 256, S::kTotal, stream>>>(ma, mb, static_cast<__nv_bfloat16*>(C), ldc, K, tiles_m, tiles_n);
+    } else {
+      auto kfn = gemm_bf16_tn_persistent_kernel<BLOCK_N, STAGES, RELU, 1>;
+      KTB_CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+      kfn<<<grid, 64 + 128, S::kTotal, stream>>>(ma, mb, static_cast<__nv_bfloat16*>(C), ldc, K, tiles_m, tiles_n);
+    }
   } else {
     auto kfn = gemm_bf16_tn_kernel<BLOCK_N, STAGES, RELU>;
     KTB_CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));

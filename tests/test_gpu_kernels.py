@@ -290,8 +290,14 @@ def test_mlp_tcgen05_matches_recorded_reference_and_fp32(K, golden):
     # staged form (row chunks pulled through a double-buffered staging area on a side stream): identical bits
     K.set_tuning(8, 4096)  # several chunks
     got3 = mlp.mlp_forward(obs2.cuda(), w1, w2, w3, staged=True).cpu().float()
-    K.set_tuning(8, 16384)
+    K.set_tuning(8, 32768)
     assert torch.equal(got3, got2)
+    for epi in (1, 2):  # one or two epilogue warpgroups: same bits
+        K.set_tuning(9, epi)
+        assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got2)
+    K.set_tuning(7, 0)  # one-tile-per-CTA kernel: same bits
+    assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got2)
+    K.set_tuning(7, 1)
     # top-1 action agrees wherever the fp32 top-2 logit gap exceeds 2^-6
     top2 = want2.topk(2, dim=1).values
     clear = (top2[:, 0] - top2[:, 1]) > 2**-6
