@@ -12,6 +12,7 @@
 #include "ktb_common.cuh"
 
 #include <algorithm>
+#include <mutex>
 
 namespace ktb {
 
@@ -108,6 +109,30 @@ int ktb_broadcast(int root, const void* src, void* const* dsts, int n_dst, size_
   return KTB_OK;
 }
 
+// Per-call events (created on the device that records them, destroyed right after the waits are enqueued:
+// CUDA releases an event's resources once pending work on it has completed). Shared per-device events would let two
+// host threads using different streams wait on each other's records.
+struct CallEvents {
+  cudaEvent_t ev[kMaxDevices + 1];
+  int dev[kMaxDevices + 1];
+  int n = 0;
+  cudaEvent_t make(int device) {
+    DeviceGuard g(device);
+    cudaEvent_t e = nullptr;
+    if (!g.ok || cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ev[n] = e;
+    dev[n] = device;
+    ++n;
+    return e;
+  }
+  ~CallEvents() {
+    for (int i = 0; i < n; ++i) {
+      DeviceGuard g(dev[i]);
+      cudaEventDestroy(ev[i]);
+    }
+  }
+};
+
 static int check_ranks(const char* who, int n_ranks, const int* devs, int root_rank) {
   KTB_REQUIRE(n_ranks > 0 && n_ranks <= kMaxDevices && devs, KTB_ERR_ARG, "%s: bad n_ranks %d", who, n_ranks);
   KTB_REQUIRE(root_rank >= 0 && root_rank < n_ranks, KTB_ERR_ARG, "%s: root_rank %d out of range", who, root_rank);
@@ -141,10 +166,14 @@ int ktb_scatter_map_gather(int op, int dtype, const void* src_root, void* dst_ro
     return streams ? reinterpret_cast<cudaStream_t>(streams[r]) : device_info(devs[r])->stream_rank;
   };
   cudaStream_t root_stream = stream_of(root_rank);
-  bool joined[kMaxDevices] = {false};
+  CallEvents events;
+  cudaEvent_t done[kMaxDevices] = {nullptr};
+  cudaEvent_t args_ready = events.make(root_dev);
+  KTB_REQUIRE(args_ready, KTB_ERR_CUDA, "ktb_scatter_map_gather: cudaEventCreate failed");
+  (void)root;
   {
     KTB_GUARD(root_dev);
-    KTB_CK(cudaEventRecord(root->ev_a, root_stream));  // args are ready on the root
+    KTB_CK(cudaEventRecord(args_ready, root_stream));  // args are ready on the root
   }
   for (int r = 0; r < n_ranks; ++r) {
     size_t b = 0, e = 0;
@@ -158,13 +187,14 @@ int ktb_scatter_map_gather(int op, int dtype, const void* src_root, void* dst_ro
     // same ordering domain as the root only if it is the same stream ON the same device (handle 0 is
     // "the default stream of whichever device is current", so handles alone do not identify a stream)
     const bool is_root = (r == root_rank) || (dev == root_dev && st == root_stream);
-    if (!is_root) KTB_CK(cudaStreamWaitEvent(st, root->ev_a, 0));
+    if (!is_root) KTB_CK(cudaStreamWaitEvent(st, args_ready, 0));
     rc = launch_map(dev, op, dtype, static_cast<const uint8_t*>(src_root) + b * es,
                     static_cast<uint8_t*>(dst_root) + b * es, e - b, p, variant, st);
     if (rc) return rc;
     if (!is_root) {
-      KTB_CK(cudaEventRecord(device_info(dev)->ev_b, st));
-      joined[r] = true;
+      done[r] = events.make(dev);
+      KTB_REQUIRE(done[r], KTB_ERR_CUDA, "ktb_scatter_map_gather: cudaEventCreate failed");
+      KTB_CK(cudaEventRecord(done[r], st));
     }
   }
   // Join on the root stream with the ROOT device current: stream handle 0 names the default stream of
@@ -172,7 +202,7 @@ int ktb_scatter_map_gather(int op, int dtype, const void* src_root, void* dst_ro
   {
     KTB_GUARD(root_dev);
     for (int r = 0; r < n_ranks; ++r)
-      if (joined[r]) KTB_CK(cudaStreamWaitEvent(root_stream, device_info(devs[r])->ev_b, 0));
+      if (done[r]) KTB_CK(cudaStreamWaitEvent(root_stream, done[r], 0));
   }
   return KTB_OK;
 }
@@ -198,10 +228,14 @@ int ktb_scatter_map_reduce(int op, int dtype, const void* src_root, size_t n_ele
     return streams ? reinterpret_cast<cudaStream_t>(streams[r]) : device_info(devs[r])->stream_rank;
   };
   cudaStream_t root_stream = stream_of(root_rank);
-  bool joined[kMaxDevices] = {false};
+  CallEvents events;
+  cudaEvent_t done[kMaxDevices] = {nullptr};
+  cudaEvent_t args_ready = events.make(root_dev);
+  KTB_REQUIRE(args_ready, KTB_ERR_CUDA, "ktb_scatter_map_reduce: cudaEventCreate failed");
+  (void)root;
   {
     KTB_GUARD(root_dev);
-    KTB_CK(cudaEventRecord(root->ev_a, root_stream));
+    KTB_CK(cudaEventRecord(args_ready, root_stream));
   }
   for (int r = 0; r < n_ranks; ++r) {
     size_t b = 0, e = 0;
@@ -214,20 +248,21 @@ int ktb_scatter_map_reduce(int op, int dtype, const void* src_root, size_t n_ele
     // same ordering domain as the root only if it is the same stream ON the same device (handle 0 is
     // "the default stream of whichever device is current", so handles alone do not identify a stream)
     const bool is_root = (r == root_rank) || (dev == root_dev && st == root_stream);
-    if (!is_root) KTB_CK(cudaStreamWaitEvent(st, root->ev_a, 0));
+    if (!is_root) KTB_CK(cudaStreamWaitEvent(st, args_ready, 0));
     KTB_REQUIRE(workspaces[r], KTB_ERR_ARG, "ktb_scatter_map_reduce: workspaces[%d] is null", r);
     // empty shards still write a zero partial (n_elems = 0 → kernel stores 0)
     rc = launch_map_reduce(dev, op, dtype, static_cast<const uint8_t*>(src_root) + b * es, e - b, p,
                            static_cast<uint8_t*>(partials_root) + (size_t)r * acc_size, workspaces[r], st);
     if (rc) return rc;
     if (!is_root) {
-      KTB_CK(cudaEventRecord(device_info(dev)->ev_b, st));
-      joined[r] = true;
+      done[r] = events.make(dev);
+      KTB_REQUIRE(done[r], KTB_ERR_CUDA, "ktb_scatter_map_reduce: cudaEventCreate failed");
+      KTB_CK(cudaEventRecord(done[r], st));
     }
   }
   KTB_GUARD(root_dev);
   for (int r = 0; r < n_ranks; ++r)
-    if (joined[r]) KTB_CK(cudaStreamWaitEvent(root_stream, device_info(devs[r])->ev_b, 0));
+    if (done[r]) KTB_CK(cudaStreamWaitEvent(root_stream, done[r], 0));
   return launch_reduce_partials(root_dev, dtype, partials_root, n_ranks, out_root, root_stream);
 }
 
@@ -317,6 +352,8 @@ int ktb_map_host_multi(int op, int dtype, const void* src_host, void* dst_host, 
       KTB_REQUIRE(devs[q] != devs[r], KTB_ERR_ARG, "ktb_map_host_multi: devices must be distinct (use ktb_map_host per rank)");
     KTB_REQUIRE(stage_in[r] && stage_out[r], KTB_ERR_ARG, "ktb_map_host_multi: rank %d has no staging buffers", r);
   }
+  static std::mutex host_multi_mu;   // the per-device copy/exec streams and events carry one call at a time
+  std::lock_guard<std::mutex> lk(host_multi_mu);
   const MapParams p = make_params(alpha, beta);
   size_t sb[kMaxDevices], sbytes[kMaxDevices], max_chunks = 0;
   for (int r = 0; r < n_ranks; ++r) {

@@ -464,9 +464,22 @@ static int mlp_run(int dev, const void* obs, size_t M, int d_in, int d_hidden, i
   __nv_bfloat16* y = static_cast<__nv_bfloat16*>(logits);
   __nv_bfloat16* stg = static_cast<__nv_bfloat16*>(stage);
   const MapParams ident = make_params(1, 0);
+  // per-call events: [0] start, [1..2] staged chunk landed (by buffer), [3..4] staging buffer consumed
+  cudaEvent_t evs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  struct EvGuard {
+    cudaEvent_t* e;
+    ~EvGuard() {
+      for (int i = 0; i < 5; ++i)
+        if (e[i]) cudaEventDestroy(e[i]);
+    }
+  } ev_guard{evs};
+  static std::mutex side_mu[kMaxDevices];   // the side stream of a device carries one staged call at a time
+  std::unique_lock<std::mutex> side_lock;
   if (stg) {
-    KTB_CK(cudaEventRecord(di->ev_a, st));          // obs is ready once prior work on `st` is done
-    KTB_CK(cudaStreamWaitEvent(side, di->ev_a, 0));
+    side_lock = std::unique_lock<std::mutex>(side_mu[dev]);
+    for (int i = 0; i < 5; ++i) KTB_CK(cudaEventCreateWithFlags(&evs[i], cudaEventDisableTiming));
+    KTB_CK(cudaEventRecord(evs[0], st));            // obs is ready once prior work on `st` is done
+    KTB_CK(cudaStreamWaitEvent(side, evs[0], 0));
   }
   size_t c = 0;
   for (size_t r0 = 0; r0 < M; r0 += chunk, ++c) {
@@ -477,16 +490,16 @@ static int mlp_run(int dev, const void* obs, size_t M, int d_in, int d_hidden, i
       // A tile d_hidden/256 times over NVLink, peer reads being uncached in the local L2)
       const int b = (int)(c & 1);
       __nv_bfloat16* dstb = stg + (size_t)b * chunk * d_in;
-      if (c >= 2) KTB_CK(cudaStreamWaitEvent(side, di->host_ev[2 + b], 0));   // GEMM 1 of chunk c-2 consumed it
+      if (c >= 2) KTB_CK(cudaStreamWaitEvent(side, evs[3 + b], 0));   // GEMM 1 of chunk c-2 consumed it
       rc = launch_map(dev, KTB_OP_IDENTITY, KTB_U8, a1, dstb, rows * (size_t)d_in * 2, ident, KTB_VARIANT_AUTO, side);
       if (rc) return rc;
-      KTB_CK(cudaEventRecord(di->host_ev[b], side));
-      KTB_CK(cudaStreamWaitEvent(st, di->host_ev[b], 0));
+      KTB_CK(cudaEventRecord(evs[1 + b], side));
+      KTB_CK(cudaStreamWaitEvent(st, evs[1 + b], 0));
       a1 = dstb;
     }
     rc = launch_gemm<256, 4, true>(a1, W1, h1, rows, d_hidden, d_in, d_hidden, st);
     if (rc) return rc;
-    if (stg) KTB_CK(cudaEventRecord(di->host_ev[2 + (int)(c & 1)], st));
+    if (stg) KTB_CK(cudaEventRecord(evs[3 + (int)(c & 1)], st));
     rc = launch_gemm<256, 4, true>(h1, W2, h2, rows, d_hidden, d_hidden, d_hidden, st);
     if (rc) return rc;
     rc = launch_gemm<64, 4, false>(h2, W3, y + r0 * d_out, rows, d_out, d_hidden, d_out, st);

@@ -250,3 +250,19 @@ def test_kt_put_get_gpu_store_patterns():
     assert kt.ls("model/weights") == []
     with pytest.raises(kt.DataStoreError, match="timed out"):
         kt.get(key="late", dest=torch.zeros(1, device="cuda:0"), broadcast=kt.BroadcastWindow(world_size=2, timeout=0.3))
+
+
+def test_results_are_fresh_tensors_not_aliases_of_a_cache():
+    double = _mapped(cases.double, "scale", alpha=2.0)
+    remote = _deploy(double, 2, "t-fresh")
+    try:
+        a = torch.arange(10, dtype=torch.float32)
+        r1 = remote(a, serialization="pickle")               # host path
+        r2 = remote(a + 100, serialization="pickle")
+        assert torch.equal(torch.cat(r1), a * 2) and torch.equal(torch.cat(r2), (a + 100) * 2)
+        d1 = remote(a.cuda(), serialization="pickle")          # device path
+        d2 = remote((a + 100).cuda(), serialization="pickle")
+        torch.cuda.synchronize()
+        assert torch.equal(torch.cat(d1).cpu(), a * 2) and torch.equal(torch.cat(d2).cpu(), (a + 100) * 2)
+    finally:
+        remote.teardown()
