@@ -137,6 +137,26 @@ def test_two_gpu_peer_path_matches_oracle():
         y = ops.scatter_map_gather(x.cuda(0), "affine", 0.5, 1.5, devices=[0, 1], variant=variant)
         torch.cuda.synchronize(0)
         assert torch.equal(y.cpu(), want), variant
+    # concurrent callers on their own streams (per-call events keep their joins apart)
+    import threading
+
+    errs = []
+
+    def worker(i):
+        try:
+            xi_ = torch.randn((1 << 20) + i, generator=torch.Generator().manual_seed(i))
+            with torch.cuda.device(0), torch.cuda.stream(torch.cuda.Stream(0)):
+                for _ in range(5):
+                    yi_ = ops.scatter_map_gather(xi_.cuda(0), "scale", float(i + 2), devices=[0, 1])
+                    torch.cuda.current_stream(0).synchronize()
+                    assert torch.equal(yi_.cpu(), xi_ * float(i + 2))
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+
+    ths = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not errs, errs
     sess = ops.PushSession([0, 1], ops.shard_bounds(x.numel(), 2, 0)[1] * 4)
     for it in range(4):  # consecutive calls exercise staging parity and the ack back-pressure
         y = torch.zeros_like(x, device="cuda:0")
