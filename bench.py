@@ -338,7 +338,10 @@ def run_ours(args):
                 "traffic": None, "peak_source": "measured peer copy per direction (B200_PROFILING.md)",
                 "kernel": "ktb::map_vec_kernel<F32,SCALE,32B> on peer pointers",
                 "algorithmic_bytes_per_launch": 2 * shard_bytes,
-                "note": "bytes crossing the root GPU's NVLink port per direction per call / step time"}
+                "note": "bytes crossing the root GPU's NVLink port per direction per call / step time; both "
+                        "directions are busy at once, where the copy engines reach 353 GB/s per direction on this pool "
+                        "(profiles/r1f_sweep_peer_2gpu.jsonl: torch_peer_copy_duplex)",
+                "duplex_copy_engine_reference": 353.4, "frac_of_duplex_reference": achieved / 353.4}
 
     # ---- e2e: public API, host buffers ---------------------------------------------------------------------------
     e2e = None

@@ -148,14 +148,18 @@ class GpuSPMDSupervisor(SPMDSupervisor):
                 if f in done and f.exception() is not None:
                     raise f.exception()
             results = []
+            touched = set()
             for r, f in zip(ranks, futures):
                 msg = f.result()
                 value = pickle.loads(msg["result"]) if isinstance(msg, dict) else pickle.loads(msg)
                 if isinstance(msg, dict) and "res_offsets" in msg:
                     value = self._gather_result(r, value, msg["res_offsets"])
+                    touched.add(self.devices[r])
                 if isinstance(msg, dict) and msg.get("res_needed"):
                     self._grow(r, "res", _round_up(msg["res_needed"] * 2))
                 results.append(value)
+            for dev in touched:  # one sync per GPU after ALL gathers are enqueued (they run concurrently)
+                torch.cuda.current_stream(dev).synchronize()
         return results
 
     def _gather_result(self, r: int, skeleton, offsets):
@@ -174,7 +178,6 @@ class GpuSPMDSupervisor(SPMDSupervisor):
         with torch.cuda.device(dev):
             arena = self.res_arenas[r].tensor(torch.uint8)
             ops.unpack(arena, offsets, outs)
-            torch.cuda.current_stream(dev).synchronize()
         return join_tensors(skeleton, outs)
 
 
