@@ -286,3 +286,25 @@ def test_results_are_fresh_tensors_not_aliases_of_a_cache():
         assert torch.equal(torch.cat(d1).cpu(), a * 2) and torch.equal(torch.cat(d2).cpu(), (a + 100) * 2)
     finally:
         remote.teardown()
+
+
+def test_edge_inputs_empty_noncontiguous_unsupported_dtype():
+    double = _mapped(cases.double, "scale", alpha=2.0)
+    remote = _deploy(double, 3, "t-edge")
+    try:
+        empty = remote(torch.empty(0).cuda(), serialization="pickle")
+        assert len(empty) == 3 and all(e.numel() == 0 for e in empty)
+        one = remote(torch.tensor([5.0]).cuda(), serialization="pickle")       # fewer rows than ranks
+        assert [o.numel() for o in one] == [1, 0, 0] and float(one[0]) == 10.0
+        x = torch.randn(7, 5)
+        xt = x.t()                                                             # non-contiguous view, 5 rows of 7
+        want = ref_dispatch.spmd_call(cases.double, xt, num_proc=3, serialization="pickle")
+        got = remote(xt.cuda(), serialization="pickle")
+        assert [tuple(g.shape) for g in got] == [tuple(w.shape) for w in want]
+        assert all(torch.equal(g.cpu(), w) for g, w in zip(got, want))
+        got_h = remote(xt, serialization="pickle")                             # same through the host path
+        assert all(torch.equal(g, w) for g, w in zip(got_h, want))
+        with pytest.raises(TypeError, match="support"):
+            remote(torch.ones(4, dtype=torch.float64).cuda(), serialization="pickle")
+    finally:
+        remote.teardown()
