@@ -31,6 +31,7 @@ constexpr int kMlpUmmaK = 16;
 constexpr int kMlpThreads = 192;
 int g_mlp_chunk_rows = 32768;  // ktb_set_tuning key 8: rows per chunk (2 x 64 MiB of hidden activations at d_hidden = 1024; measured best)
 int g_mlp_epi_groups = 1;      // ktb_set_tuning key 9: epilogue warpgroups (1 or 2); 2 measured 3% slower
+int g_mlp_tma_store = 0;       // ktb_set_tuning key 10: 1 = TMA-store epilogue for the 256-wide layers
 int g_mlp_persistent = 1;      // ktb_set_tuning key 7: 1 = persistent double-buffered kernel, 0 = one tile per CTA
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
@@ -354,6 +355,160 @@ __global__ void __launch_bounds__(64 + 128 * EPI_GROUPS)
   }
 }
 
+// Persistent kernel with a TMA-STORE epilogue (BLOCK_N = 256 layers, whose output is a plain local matrix):
+// the epilogue warps convert the accumulator to bf16 into a 128x256 shared-memory tile laid out as four
+// SWIZZLE_128B boxes of 64 columns, and one thread writes it out with cp.async.bulk.tensor (full 128-byte lines
+// instead of 16-byte stores 2 KiB apart).  Three operand stages (144 KiB) + the 64 KiB C tile fit in shared memory.
+constexpr int kEpiBarrier = 1;   // named barrier of the 128 epilogue threads
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync %0, 128;" ::"n"(kEpiBarrier) : "memory"); }
+
+template <int STAGES, bool RELU>
+__global__ void __launch_bounds__(kMlpThreads)
+    gemm_bf16_tn_tmastore_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                 const __grid_constant__ CUtensorMap map_c, int K, int tiles_m, int tiles_n) {
+  constexpr int BLOCK_N = 256;
+  using S = MlpSmem<BLOCK_N, STAGES>;
+  constexpr int kCBytes = kMlpBlockM * BLOCK_N * 2;        // 64 KiB
+  constexpr int kBoxBytes = kMlpBlockM * 64 * 2;           // one 128 x 64 box
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ctile = smem + S::kBarrierOff;                  // stages end on a 1024-byte boundary
+  uint64_t* full = reinterpret_cast<uint64_t*>(ctile + kCBytes);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = K / kMlpBlockK;
+  const int num_tiles = tiles_m * tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+    prefetch_tensormap(&map_c);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 4);
+    mbar_init(&tmem_empty[1], 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, 2 * BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * kMlpBlockM;
+        const int n0 = (tile % tiles_n) * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+          uint8_t* a_dst = smem + (size_t)s * S::kStageBytes;
+          mbar_expect_tx(&full[s], S::kStageBytes);
+          tma_load_2d(a_dst, &map_a, kb * kMlpBlockK, m0, &full[s]);
+          tma_load_2d(a_dst + S::kABytes, &map_b, kb * kMlpBlockK, n0, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kMlpBlockM, BLOCK_N);
+      int it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const int as = t & 1;
+        mbar_wait(&tmem_empty[as], ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint8_t* a_src = smem + (size_t)s * S::kStageBytes;
+          const uint64_t adesc = make_smem_desc_sw128(a_src);
+          const uint64_t bdesc = make_smem_desc_sw128(a_src + S::kABytes);
+#pragma unroll
+          for (int k = 0; k < kMlpBlockK / kMlpUmmaK; ++k)
+            umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;                    // row of the tile this thread owns
+    const bool issuer = (warp == 2 && lane == 0);
+    int t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int as = t & 1;
+      const int m0 = (tile / tiles_n) * kMlpBlockM;
+      const int n0 = (tile % tiles_n) * BLOCK_N;
+      mbar_wait(&tmem_full[as], (t >> 1) & 1);
+      tc_fence_after();
+      if (issuer) bulk_wait_read<0>();                      // the previous tile's stores have read the C tile
+      epi_barrier();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c), acc);
+        uint8_t* box = ctile + (c >> 6) * kBoxBytes + row * 128;   // this row inside the 64-column box
+        const int chunk0 = (c & 63) >> 3;                          // first 16-byte chunk (0 or 4)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float lo = __uint_as_float(acc[8 * q + 2 * j]);
+            float hi = __uint_as_float(acc[8 * q + 2 * j + 1]);
+            if (RELU) {
+              lo = fmaxf(lo, 0.f);
+              hi = fmaxf(hi, 0.f);
+            }
+            __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+            pk[j] = *reinterpret_cast<uint32_t*>(&v);
+          }
+          const int phys = (chunk0 + q) ^ (row & 7);               // SWIZZLE_128B: chunk index XOR (row mod 8)
+          *reinterpret_cast<uint4*>(box + phys * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);          // accumulator drained: the MMA warp may refill it
+      fence_proxy_async_smem();                             // generic-proxy writes → visible to the TMA store
+      epi_barrier();
+      if (issuer) {
+#pragma unroll
+        for (int b = 0; b < BLOCK_N / 64; ++b) tma_store_2d(&map_c, ctile + b * kBoxBytes, n0 + 64 * b, m0);
+        bulk_commit();
+      }
+    }
+    if (issuer) bulk_wait_all<0>();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BLOCK_N);
+  }
+}
+
 // ---- host side --------------------------------------------------------------------------------------
 typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -395,7 +550,22 @@ static int launch_gemm(const void* A, const void* B, void* C, size_t M, int N, i
   if (rc) return rc;
   rc = make_map(&mb, B, (uint64_t)N, (uint64_t)K, BLOCK_N);
   if (rc) return rc;
-  if (g_mlp_persistent) {
+  if (g_mlp_persistent && g_mlp_tma_store && BLOCK_N == 256 && ldc == N) {
+    constexpr int ST = 3;
+    using S3 = MlpSmem<256, ST>;
+    constexpr int smem_bytes = S3::kBarrierOff + kMlpBlockM * 256 * 2 + (2 * ST + 4) * 8 + 16 + 1024;
+    CUtensorMap mc;
+    rc = make_map(&mc, C, M, (uint64_t)N, kMlpBlockM);
+    if (rc) return rc;
+    auto kfn = gemm_bf16_tn_tmastore_kernel<ST, RELU>;
+    KTB_CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    const int tiles_m = (int)(M / kMlpBlockM), tiles_n = N / 256;
+    int dev = 0;
+    KTB_CK(cudaGetDevice(&dev));
+    const int sms = device_info(dev) ? device_info(dev)->sm_count : 148;
+    const int grid = std::min(tiles_m * tiles_n, sms);
+    kfn<<<grid, kMlpThreads, smem_bytes, stream>>>(ma, mb, mc, K, tiles_m, tiles_n);
+  } else if (g_mlp_persistent) {
     const int tiles_m = (int)(M / kMlpBlockM), tiles_n = N / BLOCK_N;
     int dev = 0;
     KTB_CK(cudaGetDevice(&dev));
