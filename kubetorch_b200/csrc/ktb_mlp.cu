@@ -31,7 +31,7 @@ constexpr int kMlpUmmaK = 16;
 constexpr int kMlpThreads = 192;
 int g_mlp_chunk_rows = 32768;  // ktb_set_tuning key 8: rows per chunk (2 x 64 MiB of hidden activations at d_hidden = 1024; measured best)
 int g_mlp_epi_groups = 1;      // ktb_set_tuning key 9: epilogue warpgroups (1 or 2); 2 measured 3% slower
-int g_mlp_tma_store = 0;       // ktb_set_tuning key 10: 1 = TMA-store epilogue for the 256-wide layers
+int g_mlp_tma_store = 1;       // ktb_set_tuning key 10: 1 = TMA-store epilogue for the 256-wide layers (default)
 int g_mlp_persistent = 1;      // ktb_set_tuning key 7: 1 = persistent double-buffered kernel, 0 = one tile per CTA
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
