@@ -366,6 +366,31 @@ def run_ours(args):
     if world > 1:
         dist.barrier(group=cpu_group)  # other ranks wait on the CPU while rank 0 drives all N GPUs
 
+    # ---- calls/sec on 1 KiB payloads (the other half of BASELINE.json's metric), N=1 only ------------------------
+    small = None
+    if rank == 0 and n_gpus == 1:
+        xs = [torch.randn(256, device="cuda:0") for _ in range(2048)]
+        ys = [torch.empty_like(t) for t in xs]
+        plan = ops.BatchPlan(xs, ys, "scale", 2.0)
+
+        def dev_ms(fn, iters):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                fn()
+            b2.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b2) / iters
+
+        ms_batch = dev_ms(plan.run, 20)                       # 2048 calls coalesced into segmented launches
+        ms_single = dev_ms(lambda: ops.map_tensor(xs[0], "scale", 2.0, out=ys[0]), 2000)   # one launch per call
+        small = {"payload_bytes": 1024, "one_launch_per_call_calls_per_sec": 1e3 / ms_single,
+                 "coalesced_batch_calls_per_sec": 2048 * 1e3 / ms_batch, "device_timed": True}
+        assert torch.equal(ys[5], xs[5] * 2)
+
     # ---- CPU baseline (N=1 only), bounded sample ---------------------------------------------------------------------
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
@@ -387,7 +412,7 @@ def run_ours(args):
                 "transfer": best_mode, "ms_per_step_by_transfer": modes,
                 "l2": "inputs+outputs (512 MiB) exceed the 126 MB L2; no flush needed",
             },
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "small_calls": small,
             "gpu_launches": gpu_launches,
         }
         print(json.dumps(line), flush=True)
