@@ -14,7 +14,7 @@
 namespace ktb {
 
 constexpr int kRedThreads = 256;
-constexpr int kRedMaxGrid = 2048;
+constexpr int kRedMaxGrid = 8192;
 constexpr size_t kRedHeader = 64;  // counter lives in the first 64 bytes of the workspace
 int g_red_ctas_per_sm = 8;         // ktb_set_tuning key 6
 
@@ -114,20 +114,23 @@ __global__ void __launch_bounds__(kRedThreads)
 
   A acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
   const size_t stride = (size_t)gridDim.x * kRedThreads;
-  size_t v = (size_t)blockIdx.x * kRedThreads + threadIdx.x;
-  // 4 independent 256-bit loads in flight per thread
-  for (; v + 3 * stride < n_vec; v += 4 * stride) {
+  // CTA-contiguous tiles of 4 x 256 packets (32 KiB): 4 independent 256-bit loads in flight per thread, one tile per
+  // CTA when the grid covers the input (the hardware scheduler balances the tail), grid-stride beyond kRedMaxGrid
+  constexpr size_t kTilePackets = 4 * (size_t)kRedThreads;
+  const size_t n_tiles = n_vec / kTilePackets;
+  for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const size_t v = t * kTilePackets + threadIdx.x;
     uint32_t w0[8], w1[8], w2[8], w3[8];
     ldg256_stream(src + (v << 5), w0);
-    ldg256_stream(src + ((v + stride) << 5), w1);
-    ldg256_stream(src + ((v + 2 * stride) << 5), w2);
-    ldg256_stream(src + ((v + 3 * stride) << 5), w3);
+    ldg256_stream(src + ((v + kRedThreads) << 5), w1);
+    ldg256_stream(src + ((v + 2 * kRedThreads) << 5), w2);
+    ldg256_stream(src + ((v + 3 * kRedThreads) << 5), w3);
     acc0 += words_value<DT, OP, 8>(w0, mp);
     acc1 += words_value<DT, OP, 8>(w1, mp);
     acc2 += words_value<DT, OP, 8>(w2, mp);
     acc3 += words_value<DT, OP, 8>(w3, mp);
   }
-  for (; v < n_vec; v += stride) {
+  for (size_t v = n_tiles * kTilePackets + (size_t)blockIdx.x * kRedThreads + threadIdx.x; v < n_vec; v += stride) {
     uint32_t w0[8];
     ldg256_stream(src + (v << 5), w0);
     acc0 += words_value<DT, OP, 8>(w0, mp);
@@ -178,9 +181,11 @@ template <int DT, int OP>
 static int launch_reduce_typed(int dev, const uint8_t* src, size_t n_elems, const MapParams& p,
                                void* out, void* ws, cudaStream_t stream) {
   const DeviceInfo* di = device_info(dev);
-  size_t blocks = (n_elems + (size_t)kRedThreads * 32 - 1) / ((size_t)kRedThreads * 32);
-  int grid = (int)std::min<size_t>(std::max<size_t>(blocks, 1),
-                                   std::min<size_t>((size_t)di->sm_count * g_red_ctas_per_sm, kRedMaxGrid));
+  (void)di;
+  constexpr size_t ES = (DT == KTB_BF16) ? 2 : (DT == KTB_I64 ? 8 : 4);
+  const size_t tiles = (n_elems * ES + 32767) / 32768;   // one 32 KiB tile per CTA
+  const size_t cap = g_red_ctas_per_sm > 0 ? std::min<size_t>((size_t)kRedMaxGrid, (size_t)g_red_ctas_per_sm * 1024) : kRedMaxGrid;
+  int grid = (int)std::min<size_t>(std::max<size_t>(tiles, 1), cap);
   map_reduce_kernel<DT, OP><<<grid, kRedThreads, 0, stream>>>(src, n_elems, p, out, (uint8_t*)ws);
   KTB_CK(cudaGetLastError());
   return KTB_OK;

@@ -60,9 +60,9 @@ def main():
                     ms = timeit(lambda: ops.map_tensor(x, op, 2.0, out=y, variant=L.VARIANT_VEC))
                     emit(what="map_vec", op=op, unroll=un, flavor=fl, ctas_per_sm=cps, ms=ms,
                          gbps=2 * nbytes / ms / 1e6)
-        ops.set_tuning(0, 8)
-        ops.set_tuning(4, 0)
-        ops.set_tuning(5, 4)
+        ops.set_tuning(0, 0)   # back to the defaults: one tile per CTA, evict_first, unroll 2
+        ops.set_tuning(4, 2)
+        ops.set_tuning(5, 2)
         for cfg, per_sm_opts in ((0, (1,)), (1, (1,)), (2, (1, 2)), (3, (1,))):
             for per_sm in per_sm_opts:
                 ops.set_tuning(2, cfg)
@@ -94,8 +94,11 @@ def main():
         del a, b
 
     # reduce
-    ms = timeit(lambda: ops.map_reduce_sum(x, "scale", 2.0))
-    emit(what="reduce_sum_f32_256MiB", ms=ms, gbps=nbytes / ms / 1e6)
+    for cap in (1, 2, 4, 8):
+        ops.set_tuning(6, cap)
+        ms = timeit(lambda: ops.map_reduce_sum(x, "scale", 2.0))
+        emit(what="reduce_sum_f32_256MiB", grid_cap=cap * 1024, ms=ms, gbps=nbytes / ms / 1e6)
+    ops.set_tuning(6, 8)
 
     # pack: 1024 tensors of 256 KiB, and 4096 of 4 KiB
     for cnt, sz in ((1024, 1 << 18), (4096, 1 << 12), (8, 1 << 25)):
