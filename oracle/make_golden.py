@@ -97,10 +97,32 @@ GROUPS = {
     "spmd_identity_2": ("spmd_identity", {"distribution_type": "spmd", "num_proc": 2}, "json,pickle", [
         ("broadcast_f32_3_x2", None, ["@f32_3"], {}, "pickle"),
     ]),
+    "mixed_spmd2": ("mixed_payload", {"distribution_type": "spmd", "num_proc": 2}, "json,pickle", [
+        ("mixed_payload_x2", None, ["@f32_3", {"t": "@i64_130", "tag": "hello"}], {"scale": 2}, "pickle"),
+    ]),
+    "number_spmd2": ("Number", {"distribution_type": "spmd", "num_proc": 2}, "json,pickle", [
+        ("number_spmd_add", "add", [1, 2], {}, "json"),
+        ("number_spmd_add_kwargs", "add", [], {"x": 5, "y": 6}, "json"),
+    ]),
+    "async_local": ("async_summer", {"distribution_type": "local"}, "json,pickle", [
+        ("async_summer_1", None, [1, 2], {"sleep_time": 0.01}, "json"),
+        ("async_summer_2", None, [10, 20], {"sleep_time": 0.01}, "json"),
+    ]),
     "mlp_spmd2": ("mlp_policy", {"distribution_type": "spmd", "num_proc": 2}, "json,pickle", [
         ("mlp_bf16_256_x2", None, ["@mlp_obs", "@mlp_w1", "@mlp_w2", "@mlp_w3"], {}, "pickle"),
     ]),
 }
+
+
+def _resolve(spec, inputs):
+    """Replace "@name" strings (at any depth of lists/dicts) by the named input tensor."""
+    if isinstance(spec, str) and spec.startswith("@"):
+        return inputs[spec[1:]]
+    if isinstance(spec, list):
+        return [_resolve(v, inputs) for v in spec]
+    if isinstance(spec, dict):
+        return {k: _resolve(v, inputs) for k, v in spec.items()}
+    return spec
 
 
 def run_group(group: str, out_path: str):
@@ -125,7 +147,7 @@ def run_group(group: str, out_path: str):
     results = {}
     with TestClient(app, raise_server_exceptions=False) as client:
         for case, method, arg_spec, kwargs, ser in cases:
-            args = [inputs[a[1:]] if isinstance(a, str) and a.startswith("@") else a for a in arg_spec]
+            args = _resolve(arg_spec, inputs)
             body = _serialize_body(build_call_body(*args, **dict(kwargs)), ser)
             url = f"/{name}/{method}" if method else f"/{name}"
             resp = client.post(url, json=body, headers={"X-Serialization": ser, "X-Request-ID": case})
@@ -159,7 +181,10 @@ def main():
     env["HOME"] = work
     env["PYTHONDONTWRITEBYTECODE"] = "1"
     all_results = {}
-    for group in GROUPS:
+    only = [a for a in sys.argv[1:] if a in GROUPS]
+    if only and os.path.exists(OUT):
+        all_results.update(torch.load(OUT, weights_only=False)["cases"])   # keep the other groups' records
+    for group in (only or GROUPS):
         out_path = os.path.join(work, f"{group}.pkl")
         print(f"[make_golden] {group} ...", flush=True)
         subprocess.run([sys.executable, os.path.abspath(__file__), "--group", group, out_path], env=env, check=True,

@@ -29,7 +29,14 @@ def golden():
 
 
 def resolve_args(fx, arg_spec):
-    return [fx["all_inputs"][a[1:]] if isinstance(a, str) and a.startswith("@") else a for a in arg_spec]
+    """Replace "@name" strings (at any depth of lists/dicts) by the named golden input tensor."""
+    if isinstance(arg_spec, str) and arg_spec.startswith("@"):
+        return fx["all_inputs"][arg_spec[1:]]
+    if isinstance(arg_spec, list):
+        return [resolve_args(fx, v) for v in arg_spec]
+    if isinstance(arg_spec, dict):
+        return {k: resolve_args(fx, v) for k, v in arg_spec.items()}
+    return arg_spec
 
 
 def mapped_copy(fn, *a, **k):

@@ -68,9 +68,11 @@ def test_reference_asset_goldens_through_api(deployed):
 def _same(a, b):
     if isinstance(a, torch.Tensor):
         return isinstance(b, torch.Tensor) and a.dtype == b.dtype and a.shape == b.shape and \
-            torch.equal(a.contiguous().view(torch.uint8), b.contiguous().view(torch.uint8))
+            torch.equal(a.contiguous().reshape(-1).view(torch.uint8), b.contiguous().reshape(-1).view(torch.uint8))
     if isinstance(a, (list, tuple)):
-        return len(a) == len(b) and all(_same(x, y) for x, y in zip(a, b))
+        return isinstance(b, (list, tuple)) and len(a) == len(b) and all(_same(x, y) for x, y in zip(a, b))
+    if isinstance(a, dict):
+        return isinstance(b, dict) and a.keys() == b.keys() and all(_same(a[k], b[k]) for k in a)
     return a == b
 
 
