@@ -24,6 +24,7 @@ extern int g_mlp_persistent;   // ktb_mlp.cu
 extern int g_mlp_chunk_rows;   // ktb_mlp.cu
 extern int g_mlp_epi_groups;   // ktb_mlp.cu
 extern int g_mlp_tma_store;    // ktb_mlp.cu
+extern int g_mlp_2sm;          // ktb_mlp.cu
 
 // ---- tunables (ktb_set_tuning) ---------------------------------------------------------------
 static std::atomic<int> g_vec_ctas_per_sm{0};  // 0 = one tile per CTA (measured best, profiles/r1_sweep.md)
@@ -360,6 +361,7 @@ int ktb_set_tuning(int key, int value) {
     case 7: g_mlp_persistent = value ? 1 : 0; return KTB_OK;
     case 9: g_mlp_epi_groups = (value == 2) ? 2 : 1; return KTB_OK;
     case 10: g_mlp_tma_store = value ? 1 : 0; return KTB_OK;
+    case 11: g_mlp_2sm = value ? 1 : 0; return KTB_OK;
     case 8:
       KTB_REQUIRE(value > 0 && value % 128 == 0, KTB_ERR_ARG, "ktb_set_tuning: MLP chunk rows must be a multiple of 128");
       g_mlp_chunk_rows = value;

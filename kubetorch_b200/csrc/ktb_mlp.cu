@@ -31,6 +31,7 @@ constexpr int kMlpUmmaK = 16;
 constexpr int kMlpThreads = 192;
 int g_mlp_chunk_rows = 32768;  // ktb_set_tuning key 8: rows per chunk (2 x 64 MiB of hidden activations at d_hidden = 1024; measured best)
 int g_mlp_epi_groups = 1;      // ktb_set_tuning key 9: epilogue warpgroups (1 or 2); 2 measured 3% slower
+int g_mlp_2sm = 0;             // ktb_set_tuning key 11: 1 = CTA-pair (cta_group::2) kernel for the 256-wide layers
 int g_mlp_tma_store = 1;       // ktb_set_tuning key 10: 1 = TMA-store epilogue for the 256-wide layers (default)
 int g_mlp_persistent = 1;      // ktb_set_tuning key 7: 1 = persistent double-buffered kernel, 0 = one tile per CTA
 
@@ -509,6 +510,247 @@ __global__ void __launch_bounds__(kMlpThreads)
   }
 }
 
+// ---- 2-SM form: a CTA PAIR (cluster of 2) computes a 256 x 256 tile with tcgen05.mma.cta_group::2 -------------
+// Why: with one CTA per tile the 128x256x16 UMMA reads 12 KiB of operands from shared memory per 128 cycles while TMA
+// refills 48 KiB per k-block — 192 B/clk against a 128 B/clk shared-memory port (tensor pipe <= 67 %; measured 58 %).
+// In a pair each CTA holds ITS 128 rows of A and HALF of B (128 of the 256 N rows): 64 + 64 B/clk, the port's limit.
+//   * both CTAs run a TMA producer: own A rows + own half of B into own shared memory, all transaction bytes
+//     reported to the LEADER's full barrier (cp.async.bulk.tensor...cta_group::2, barrier address with the peer
+//     bit cleared);
+//   * only the leader issues tcgen05.mma.cta_group::2 (M = 256); the hardware reads A/B from both CTAs at the same
+//     shared-memory offsets and writes rows 0-127 to the leader's TMEM, rows 128-255 to the peer's;
+//   * tcgen05.commit...multicast::cluster releases the stage in BOTH CTAs and publishes the accumulator to both
+//     epilogues; each CTA's epilogue drains its own TMEM half through a swizzled shared C tile + TMA store and
+//     arrives on the leader's tmem_empty barrier (the peer via mapa).
+// Every wait is bounded (trap instead of hanging the GPU if the protocol were ever violated).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  __syncwarp();   // .aligned: the whole warp must arrive together (role branches leave lanes diverged)
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                                uint32_t leader_bar_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(map), "r"(leader_bar_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_holder, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <int STAGES, bool RELU>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads)
+    gemm_bf16_tn_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                            const __grid_constant__ CUtensorMap map_c, int K, int tiles_m, int tiles_n) {
+  constexpr int BLOCK_N = 256;                              // per pair; each CTA stages 128 of these B rows
+  constexpr int kABytes = kMlpBlockM * kMlpBlockK * 2;      // 16 KiB: this CTA's 128 rows of A
+  constexpr int kBBytes = 128 * kMlpBlockK * 2;             // 16 KiB: this CTA's half of B
+  constexpr int kStageBytes = kABytes + kBBytes;            // 32 KiB per CTA per stage
+  constexpr int kCBytes = kMlpBlockM * BLOCK_N * 2;         // 64 KiB C tile of this CTA (128 rows x 256 cols)
+  constexpr int kBoxBytes = kMlpBlockM * 64 * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ctile = smem + STAGES * kStageBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ctile + kCBytes);   // used on the leader only
+  uint64_t* empty = full + STAGES;                                  // per CTA
+  uint64_t* tmem_full = empty + STAGES;                             // [2], per CTA
+  uint64_t* tmem_empty = tmem_full + 2;                             // [2], used on the leader only
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int num_kb = K / kMlpBlockK;
+  const int num_tiles = tiles_m * tiles_n;                 // 256 x 256 tiles
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+    prefetch_tensormap(&map_c);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 2);          // one arrive.expect_tx per CTA of the pair
+      mbar_init(&empty[s], 1);         // one multicast commit
+    }
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 8);      // 4 epilogue warps x 2 CTAs
+    mbar_init(&tmem_empty[1], 8);
+    fence_barrier_init();
+  }
+  cluster_sync_all();                  // barriers of both CTAs are initialised before anyone signals across
+  if (warp == 1) tmem_alloc_2sm(tmem_holder, 2 * BLOCK_N);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile / tiles_n) * 256 + (int)rank * 128;
+        const int n0 = (tile % tiles_n) * BLOCK_N + (int)rank * 128;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait_bounded(&empty[s], ((it / STAGES) & 1) ^ 1);
+          uint8_t* a_dst = smem + (size_t)s * kStageBytes;
+          const uint32_t leader_full = map_to_cta(smem_u32(&full[s]), 0);
+          mbar_expect_tx_cluster(leader_full, kStageBytes);
+          const uint32_t leader_full_tma = smem_u32(&full[s]) & 0xFEFFFFFFu;   // peer bit cleared → CTA 0's barrier
+          tma_load_2d_2sm(a_dst, &map_a, kb * kMlpBlockK, m0, leader_full_tma);
+          tma_load_2d_2sm(a_dst + kABytes, &map_b, kb * kMlpBlockK, n0, leader_full_tma);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N);
+      int it = 0, t = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++t) {
+        const int as = t & 1;
+        mbar_wait_bounded(&tmem_empty[as], ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait_bounded(&full[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint8_t* a_src = smem + (size_t)s * kStageBytes;
+          const uint64_t adesc = make_smem_desc_sw128(a_src);
+          const uint64_t bdesc = make_smem_desc_sw128(a_src + kABytes);
+#pragma unroll
+          for (int k = 0; k < kMlpBlockK / kMlpUmmaK; ++k)
+            umma_f16_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          umma_commit_2sm(&empty[s]);          // stage free in both CTAs
+        }
+        umma_commit_2sm(&tmem_full[as]);       // accumulator ready in both CTAs
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): own TMEM half → bf16 → swizzled shared C tile → TMA store =====
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const bool issuer = (warp == 2 && lane == 0);
+    int t = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++t) {
+      const int as = t & 1;
+      const int m0 = (tile / tiles_n) * 256 + (int)rank * 128;
+      const int n0 = (tile % tiles_n) * BLOCK_N;
+      mbar_wait_bounded(&tmem_full[as], (t >> 1) & 1);
+      tc_fence_after();
+      if (issuer) bulk_wait_read<0>();
+      epi_barrier();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c), acc);
+        uint8_t* box = ctile + (c >> 6) * kBoxBytes + row * 128;
+        const int chunk0 = (c & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float lo = __uint_as_float(acc[8 * q + 2 * j]);
+            float hi = __uint_as_float(acc[8 * q + 2 * j + 1]);
+            if (RELU) {
+              lo = fmaxf(lo, 0.f);
+              hi = fmaxf(hi, 0.f);
+            }
+            __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+            pk[j] = *reinterpret_cast<uint32_t*>(&v);
+          }
+          const int phys = (chunk0 + q) ^ (row & 7);
+          *reinterpret_cast<uint4*>(box + phys * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));   // leader's barrier
+      fence_proxy_async_smem();
+      epi_barrier();
+      if (issuer) {
+#pragma unroll
+        for (int b = 0; b < BLOCK_N / 64; ++b) tma_store_2d(&map_c, ctile + b * kBoxBytes, n0 + 64 * b, m0);
+        bulk_commit();
+      }
+    }
+    if (issuer) bulk_wait_all<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                  // both CTAs are done with TMEM and with each other's barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 2 * BLOCK_N);
+  }
+}
+
 // ---- host side --------------------------------------------------------------------------------------
 typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -550,7 +792,23 @@ static int launch_gemm(const void* A, const void* B, void* C, size_t M, int N, i
   if (rc) return rc;
   rc = make_map(&mb, B, (uint64_t)N, (uint64_t)K, BLOCK_N);
   if (rc) return rc;
-  if (g_mlp_persistent && g_mlp_tma_store && BLOCK_N == 256 && ldc == N) {
+  if (g_mlp_persistent && g_mlp_2sm && BLOCK_N == 256 && ldc == N && M % 256 == 0) {
+    constexpr int ST = 4;
+    constexpr int smem_bytes = ST * 32768 + kMlpBlockM * 256 * 2 + (2 * ST + 4) * 8 + 16 + 1024;
+    CUtensorMap mb2, mc;
+    rc = make_map(&mb2, B, (uint64_t)N, (uint64_t)K, 128);     // each CTA of the pair loads half of the B tile
+    if (rc) return rc;
+    rc = make_map(&mc, C, M, (uint64_t)N, kMlpBlockM);
+    if (rc) return rc;
+    auto kfn = gemm_bf16_tn_2sm_kernel<ST, RELU>;
+    KTB_CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    const int tiles_m = (int)(M / 256), tiles_n = N / 256;
+    int dev = 0;
+    KTB_CK(cudaGetDevice(&dev));
+    const int sms = device_info(dev) ? device_info(dev)->sm_count : 148;
+    const int grid = std::max(2, std::min(2 * tiles_m * tiles_n, sms & ~1));
+    kfn<<<grid, kMlpThreads, smem_bytes, stream>>>(ma, mb2, mc, K, tiles_m, tiles_n);
+  } else if (g_mlp_persistent && g_mlp_tma_store && BLOCK_N == 256 && ldc == N) {
     constexpr int ST = 3;
     using S3 = MlpSmem<256, ST>;
     constexpr int smem_bytes = S3::kBarrierOff + kMlpBlockM * 256 * 2 + (2 * ST + 4) * 8 + 16 + 1024;
