@@ -631,7 +631,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads)
     prefetch_tensormap(&map_c);
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 2);          // one arrive.expect_tx per CTA of the pair
+      mbar_init(&full[s], 1);          // the leader's producer arms it with the bytes of BOTH CTAs' loads
       mbar_init(&empty[s], 1);         // one multicast commit
     }
     mbar_init(&tmem_full[0], 1);
@@ -658,8 +658,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads)
           const int s = it % STAGES;
           mbar_wait_bounded(&empty[s], ((it / STAGES) & 1) ^ 1);
           uint8_t* a_dst = smem + (size_t)s * kStageBytes;
-          const uint32_t leader_full = map_to_cta(smem_u32(&full[s]), 0);
-          mbar_expect_tx_cluster(leader_full, kStageBytes);
+          // The leader expects the bytes of all four loads of this k-block (its own two and the peer's two); the
+          // peer's complete_tx may land first (the tx-count goes transiently negative, the phase cannot complete
+          // before the leader's arrive).  No remote arrive sits on the peer's critical path.
+          if (leader) mbar_expect_tx(&full[s], 2 * kStageBytes);
           const uint32_t leader_full_tma = smem_u32(&full[s]) & 0xFEFFFFFFu;   // peer bit cleared → CTA 0's barrier
           tma_load_2d_2sm(a_dst, &map_a, kb * kMlpBlockK, m0, leader_full_tma);
           tma_load_2d_2sm(a_dst + kABytes, &map_b, kb * kMlpBlockK, n0, leader_full_tma);
