@@ -368,6 +368,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                : "memory");
 }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync %0, 128;" ::"n"(kEpiBarrier) : "memory"); }
+template <int NTHREADS>
+__device__ __forceinline__ void epi_barrier_n() {
+  asm volatile("bar.sync %0, %1;" ::"n"(kEpiBarrier), "n"(NTHREADS) : "memory");
+}
 
 template <int STAGES, bool RELU>
 __global__ void __launch_bounds__(kMlpThreads)
@@ -597,8 +601,8 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-template <int STAGES, bool RELU>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads)
+template <int STAGES, bool RELU, int EPI_GROUPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * EPI_GROUPS)
     gemm_bf16_tn_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                             const __grid_constant__ CUtensorMap map_c, int K, int tiles_m, int tiles_n) {
   constexpr int BLOCK_N = 256;                              // per pair; each CTA stages 128 of these B rows
@@ -636,8 +640,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads)
     }
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], 8);      // 4 epilogue warps x 2 CTAs
-    mbar_init(&tmem_empty[1], 8);
+    mbar_init(&tmem_empty[0], 8 * EPI_GROUPS);      // 4 epilogue warps per group x 2 CTAs
+    mbar_init(&tmem_empty[1], 8 * EPI_GROUPS);
     fence_barrier_init();
   }
   cluster_sync_all();                  // barriers of both CTAs are initialised before anyone signals across
@@ -697,6 +701,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads)
     // ===== epilogue (both CTAs): own TMEM half → bf16 → swizzled shared C tile → TMA store =====
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
+    const int group = (warp - 2) >> 2;                     // each warpgroup converts its slice of the columns
+    constexpr int kColsPerGroup = BLOCK_N / EPI_GROUPS;
     const bool issuer = (warp == 2 && lane == 0);
     int t = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++t) {
@@ -706,9 +712,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads)
       mbar_wait_bounded(&tmem_full[as], (t >> 1) & 1);
       tc_fence_after();
       if (issuer) bulk_wait_read<0>();
-      epi_barrier();
+      epi_barrier_n<128 * EPI_GROUPS>();
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
+      for (int c = group * kColsPerGroup; c < (group + 1) * kColsPerGroup; c += 32) {
         uint32_t acc[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c), acc);
         uint8_t* box = ctile + (c >> 6) * kBoxBytes + row * 128;
@@ -735,7 +741,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads)
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));   // leader's barrier
       fence_proxy_async_smem();
-      epi_barrier();
+      epi_barrier_n<128 * EPI_GROUPS>();
       if (issuer) {
 #pragma unroll
         for (int b = 0; b < BLOCK_N / 64; ++b) tma_store_2d(&map_c, ctile + b * kBoxBytes, n0 + 64 * b, m0);
@@ -802,14 +808,20 @@ static int launch_gemm(const void* A, const void* B, void* C, size_t M, int N, i
     if (rc) return rc;
     rc = make_map(&mc, C, M, (uint64_t)N, kMlpBlockM);
     if (rc) return rc;
-    auto kfn = gemm_bf16_tn_2sm_kernel<ST, RELU>;
-    KTB_CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     const int tiles_m = (int)(M / 256), tiles_n = N / 256;
     int dev = 0;
     KTB_CK(cudaGetDevice(&dev));
     const int sms = device_info(dev) ? device_info(dev)->sm_count : 148;
     const int grid = std::max(2, std::min(2 * tiles_m * tiles_n, sms & ~1));
-    kfn<<<grid, kMlpThreads, smem_bytes, stream>>>(ma, mb2, mc, K, tiles_m, tiles_n);
+    if (g_mlp_epi_groups == 2) {
+      auto kfn = gemm_bf16_tn_2sm_kernel<ST, RELU, 2>;
+      KTB_CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      kfn<<<grid, 64 + 256, smem_bytes, stream>>>(ma, mb2, mc, K, tiles_m, tiles_n);
+    } else {
+      auto kfn = gemm_bf16_tn_2sm_kernel<ST, RELU, 1>;
+      KTB_CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      kfn<<<grid, 64 + 128, smem_bytes, stream>>>(ma, mb2, mc, K, tiles_m, tiles_n);
+    }
   } else if (g_mlp_persistent && g_mlp_tma_store && BLOCK_N == 256 && ldc == N) {
     constexpr int ST = 3;
     using S3 = MlpSmem<256, ST>;

@@ -299,7 +299,10 @@ def test_mlp_tcgen05_matches_recorded_reference_and_fp32(K, golden):
     K.set_tuning(10, 1)  # TMA-store epilogue (swizzled shared-memory C tile): same bits
     assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got2)
     K.set_tuning(11, 1)  # CTA-pair kernel (tcgen05.mma.cta_group::2, 256x256 tiles): same bits
-    assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got2)
+    for epi in (1, 2):
+        K.set_tuning(9, epi)
+        assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got2)
+    K.set_tuning(9, 1)
     K.set_tuning(11, 0)
     K.set_tuning(10, 0)
     K.set_tuning(7, 0)  # one-tile-per-CTA kernel: same bits

@@ -31,10 +31,10 @@ def main():
     w2 = (torch.randn(1024, 1024, device="cuda", generator=g) * 0.02).bfloat16()
     w3 = (torch.randn(64, 1024, device="cuda", generator=g) * 0.02).bfloat16()
     flop_per_row = 2 * (256 * 1024 + 1024 * 1024 + 1024 * 64)
-    for M, chunk, tst, two_sm in ((262144, 32768, 1, 0), (262144, 16384, 1, 1), (262144, 32768, 1, 1),
-                                  (262144, 65536, 1, 1), (2097152, 32768, 1, 0), (2097152, 32768, 1, 1),
-                                  (2097152, 65536, 1, 1)):
-        persistent, epi = 1, 1
+    for M, chunk, tst, two_sm, epi in ((262144, 32768, 1, 0, 1), (262144, 32768, 1, 1, 1), (262144, 32768, 1, 1, 2),
+                                       (262144, 65536, 1, 1, 1), (262144, 65536, 1, 1, 2), (2097152, 65536, 1, 1, 1),
+                                       (2097152, 65536, 1, 1, 2), (2097152, 131072, 1, 1, 2)):
+        persistent = 1
         ops.set_tuning(7, persistent)
         ops.set_tuning(8, chunk)
         ops.set_tuning(9, epi)
