@@ -29,9 +29,10 @@ constexpr int kMlpBlockM = 128;
 constexpr int kMlpBlockK = 64;   // 64 bf16 = 128 bytes = one SWIZZLE_128B row
 constexpr int kMlpUmmaK = 16;
 constexpr int kMlpThreads = 192;
-int g_mlp_chunk_rows = 32768;  // ktb_set_tuning key 8: rows per chunk (2 x 64 MiB of hidden activations at d_hidden = 1024; measured best)
+int g_mlp_chunk_rows = 65536;  // ktb_set_tuning key 8: rows per chunk (2 x 128 MiB of hidden activations at d_hidden = 1024;
+                               // measured best with the CTA-pair kernel: 940-964 TFLOP/s)
 int g_mlp_epi_groups = 1;      // ktb_set_tuning key 9: epilogue warpgroups (1 or 2); 2 measured 3% slower
-int g_mlp_2sm = 0;             // ktb_set_tuning key 11: 1 = CTA-pair (cta_group::2) kernel for the 256-wide layers
+int g_mlp_2sm = 1;             // ktb_set_tuning key 11: 1 = CTA-pair (cta_group::2) kernel for the 256-wide layers (default)
 int g_mlp_tma_store = 1;       // ktb_set_tuning key 10: 1 = TMA-store epilogue for the 256-wide layers (default)
 int g_mlp_persistent = 1;      // ktb_set_tuning key 7: 1 = persistent double-buffered kernel, 0 = one tile per CTA
 
@@ -899,7 +900,8 @@ static int mlp_run(int dev, const void* obs, size_t M, int d_in, int d_hidden, i
   DeviceInfo* di = device_info(dev);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaStream_t side = di->stream_exec;   // pulls the next chunk while this one computes
-  const size_t chunk = std::min<size_t>(M, (size_t)g_mlp_chunk_rows);
+  // staged (NVLink pull) calls use smaller chunks: the first pull is exposed and more chunks overlap better
+  const size_t chunk = std::min<size_t>(M, stage ? std::min<size_t>((size_t)g_mlp_chunk_rows, 32768) : (size_t)g_mlp_chunk_rows);
   __nv_bfloat16* h1 = static_cast<__nv_bfloat16*>(scratch);
   __nv_bfloat16* h2 = h1 + chunk * (size_t)d_hidden;
   const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(obs);

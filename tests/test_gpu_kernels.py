@@ -290,7 +290,7 @@ def test_mlp_tcgen05_matches_recorded_reference_and_fp32(K, golden):
     # staged form (row chunks pulled through a double-buffered staging area on a side stream): identical bits
     K.set_tuning(8, 4096)  # several chunks
     got3 = mlp.mlp_forward(obs2.cuda(), w1, w2, w3, staged=True).cpu().float()
-    K.set_tuning(8, 32768)
+    K.set_tuning(8, 65536)
     assert torch.equal(got3, got2)
     for epi in (1, 2):  # one or two epilogue warpgroups: same bits
         K.set_tuning(9, epi)
