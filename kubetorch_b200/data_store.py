@@ -16,6 +16,11 @@ local GPUs) and the data path by libktb200 kernels:
                                 every getter GPU's arena) → ktb_unpack on each getter GPU
                    pack=False → one segmented pull per getter
 Filesystem keys (rsync store) are a Kubernetes feature and raise NotImplementedError.
+
+Across rank PROCESSES (the reference's real usage: one pod puts, another gets): when KTB_STORE_DIR is set — the GPU
+SPMD supervisor sets it for its rank processes — `put` additionally publishes each leaf through a library arena
+(one device copy + CUDA IPC handle + a small descriptor file under KTB_STORE_DIR, the stand-in for the metadata
+server), and `get` in another process opens the handle and pulls with the same segmented kernel.
 """
 from __future__ import annotations
 
@@ -23,6 +28,10 @@ import threading
 import time
 from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Tuple, Union
+
+import hashlib
+import json
+import os
 
 from .exceptions import DataStoreError
 
@@ -118,6 +127,77 @@ _registry: Dict[str, _Entry] = {}
 _groups: Dict[str, _Group] = {}
 
 
+# ---- cross-process registry (descriptor files + CUDA IPC arenas) ---------------------------------------------
+_shared_arenas: Dict[str, Any] = {}     # full_key -> Arena owned by this process
+_opened: Dict[str, int] = {}            # handle hex -> mapped device pointer in this process
+
+
+def _store_dir() -> Optional[str]:
+    d = os.environ.get("KTB_STORE_DIR")
+    if d:
+        os.makedirs(d, exist_ok=True)
+    return d or None
+
+
+def _desc_path(d: str, full_key: str) -> str:
+    return os.path.join(d, hashlib.sha1(full_key.encode()).hexdigest() + ".json")
+
+
+def _publish_shared(full_key: str, t) -> None:
+    """Copy the leaf into an IPC-exportable arena and write its descriptor (visible to other rank processes)."""
+    import torch
+
+    from .device import ops
+
+    d = _store_dir()
+    if d is None:
+        return
+    dev = t.device.index
+    nbytes = max(t.numel() * t.element_size(), 1)
+    old = _shared_arenas.pop(full_key, None)
+    if old is not None:
+        old.free()
+    arena = ops.Arena(dev, nbytes)
+    with torch.cuda.device(dev):
+        if t.numel():
+            ops.map_tensor(t.contiguous().reshape(-1).view(torch.uint8), "identity",
+                           out=arena.tensor(torch.uint8, t.numel() * t.element_size()))
+        torch.cuda.current_stream(dev).synchronize()     # bytes are in HBM before the descriptor becomes visible
+    _shared_arenas[full_key] = arena
+    desc = {"key": full_key, "dtype": str(t.dtype).replace("torch.", ""), "shape": list(t.shape), "device": dev,
+            "nbytes": t.numel() * t.element_size(), "handle": arena.export().hex(), "pid": os.getpid()}
+    tmp = _desc_path(d, full_key) + f".{os.getpid()}.tmp"
+    with open(tmp, "w") as f:
+        json.dump(desc, f)
+    os.replace(tmp, _desc_path(d, full_key))
+
+
+def _lookup_shared(full_key: str):
+    """A (tensor view, None) of another process's published leaf, or None."""
+    import torch
+
+    from .device import ops
+
+    d = _store_dir()
+    if d is None or not os.path.exists(_desc_path(d, full_key)):
+        return None
+    with open(_desc_path(d, full_key)) as f:
+        desc = json.load(f)
+    if desc["pid"] == os.getpid():
+        return None
+    dev = torch.cuda.current_device()
+    ptr = _opened.get(desc["handle"])
+    if ptr is None:
+        ptr = _opened[desc["handle"]] = ops.ipc_open(dev, bytes.fromhex(desc["handle"]))
+    holder = type("_CAI", (), {})()
+    holder.__cuda_array_interface__ = {"shape": (max(desc["nbytes"], 1),), "typestr": "|u1", "data": (ptr, False),
+                                       "version": 3}
+    flat = torch.as_tensor(holder, device=f"cuda:{dev}")[:desc["nbytes"]]
+    dtype = getattr(torch, desc["dtype"])
+    return flat.view(dtype).reshape(desc["shape"]) if desc["nbytes"] else torch.empty(desc["shape"], dtype=dtype,
+                                                                                        device=f"cuda:{dev}")
+
+
 def _full_key(key: str, tensor_key: str) -> str:
     return f"{key}/{tensor_key}" if tensor_key else key
 
@@ -205,6 +285,9 @@ def put(key: Union[str, List[str]], src=None, locale: str = "store", broadcast: 
             with torch.cuda.device(t.device):
                 ev.record(torch.cuda.current_stream(t.device))
             _registry[_full_key(key, tk)] = _Entry(t, ev)
+    if _store_dir() is not None:
+        for tk, t in leaves:
+            _publish_shared(_full_key(key, tk), t)
     if broadcast is not None:
         return _join(key, leaves, broadcast, role="put")
     return None
@@ -226,7 +309,12 @@ def get(key: Union[str, List[str]], dest=None, broadcast: Optional[BroadcastWind
             fk = _full_key(key, tk)
             ent = _registry.get(fk)
             if ent is None:
-                raise DataStoreError(f"Key '{fk}' not found in the GPU data store")
+                remote = _lookup_shared(fk)           # published by another rank process
+                if remote is None:
+                    raise DataStoreError(f"Key '{fk}' not found in the GPU data store")
+                _check_pair(fk, remote, d)
+                pairs.append((remote, None, d))
+                continue
             _check_pair(fk, ent.tensor, d)
             pairs.append((ent.tensor, ent.event, d))
     _pull(pairs)
@@ -235,16 +323,34 @@ def get(key: Union[str, List[str]], dest=None, broadcast: Optional[BroadcastWind
 
 def ls(key: str = "", verbose: bool = False, namespace: Optional[str] = None, **_) -> List[str]:
     with _lock:
-        return sorted(k for k in _registry if k.startswith(key))
+        keys = {k for k in _registry if k.startswith(key)}
+    d = _store_dir()
+    if d is not None:
+        for name in os.listdir(d):
+            if name.endswith(".json"):
+                try:
+                    with open(os.path.join(d, name)) as f:
+                        k = json.load(f)["key"]
+                    if k.startswith(key):
+                        keys.add(k)
+                except (OSError, ValueError, KeyError):
+                    pass
+    return sorted(keys)
 
 
 def rm(key: str, recursive: bool = False, verbose: bool = False, namespace: Optional[str] = None, **_) -> None:
     with _lock:
         victims = [k for k in _registry if k == key or k.startswith(key + "/")]
-        if not victims:
+        shared = [k for k in list(_shared_arenas) if k == key or k.startswith(key + "/")]
+        if not victims and not shared:
             raise DataStoreError(f"Key '{key}' not found in the GPU data store")
         for k in victims:
             del _registry[k]
+        d = _store_dir()
+        for k in shared:
+            _shared_arenas.pop(k).free()
+            if d is not None and os.path.exists(_desc_path(d, k)):
+                os.remove(_desc_path(d, k))
 
 
 # ---- BroadcastWindow quorum (threads of the controller process) ------------------------------------------------

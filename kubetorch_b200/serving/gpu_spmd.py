@@ -14,6 +14,7 @@ allocated lazily on the first call that carries CUDA tensors, so launcher-only j
 """
 from __future__ import annotations
 
+import os
 import pickle
 import threading
 from concurrent.futures import FIRST_EXCEPTION, wait
@@ -46,6 +47,12 @@ class GpuSPMDSupervisor(SPMDSupervisor):
             self.devices = [r % max(n_dev, 1) for r in range(self.world_size)]
         pod_names = [f"{self.name}-{r // self.num_proc}" for r in range(self.world_size)]
         gpu_cfgs = [{"device": d} for d in self.devices] if n_dev else None
+        if n_dev and "KTB_STORE_DIR" not in self.env_vars:
+            import tempfile
+
+            base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+            self._store_dir = tempfile.mkdtemp(prefix=f"ktb200_store_{os.getpid()}_", dir=base)
+            self.env_vars["KTB_STORE_DIR"] = self._store_dir   # kt.put / kt.get between the rank processes
         self.pool = ProcessPool(
             self.world_size, self.pointers, self.init_args, self.name, max_threads_per_proc=self.max_threads_per_proc,
             base_env=self.env_vars, allowed_serialization=self.allowed_serialization, pod_names=pod_names,
@@ -61,6 +68,12 @@ class GpuSPMDSupervisor(SPMDSupervisor):
                 pass
         self.arg_arenas, self.res_arenas = [], []
         self._pending_updates = {}
+        if getattr(self, "_store_dir", None):
+            import shutil
+
+            shutil.rmtree(self._store_dir, ignore_errors=True)
+            self.env_vars.pop("KTB_STORE_DIR", None)
+            self._store_dir = None
 
     # ---- arenas --------------------------------------------------------------------------------------------
     def _ensure_arenas(self, arg_bytes: int):

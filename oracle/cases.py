@@ -141,3 +141,31 @@ def mixed_payload(x, meta, scale=1):
     returns this rank's view of the inputs."""
     r, w = _rank_world()
     return {"rank": r, "sum": x.sum() * scale, "y": meta["t"] + r, "tag": meta["tag"], "shape": list(x.shape)}
+
+
+def store_put_by_rank(n):
+    """Every rank publishes a tensor filled with its rank (tests/assets/kv_store/gpu_helper.py:303-351 pattern)."""
+    import torch
+
+    import kubetorch_b200 as kt
+
+    r, _ = _rank_world()
+    t = torch.full((n,), float(r), device=f"cuda:{torch.cuda.current_device()}")
+    kt.put(key=f"by-rank/{r}", src=t)
+    _KEEP.append(t)
+    return r
+
+
+def store_get_from_rank(src_rank, n):
+    """Every rank fetches the tensor another rank published; returns (sum, listing)."""
+    import torch
+
+    import kubetorch_b200 as kt
+
+    dest = torch.zeros(n, device=f"cuda:{torch.cuda.current_device()}")
+    kt.get(key=f"by-rank/{src_rank}", dest=dest)
+    torch.cuda.synchronize()
+    return [float(dest.sum()), kt.ls("by-rank")]
+
+
+_KEEP = []

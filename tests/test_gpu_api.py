@@ -308,3 +308,28 @@ def test_edge_inputs_empty_noncontiguous_unsupported_dtype():
             remote(torch.ones(4, dtype=torch.float64).cuda(), serialization="pickle")
     finally:
         remote.teardown()
+
+
+def test_kt_put_get_between_rank_processes():
+    """kt.put in one rank process, kt.get in another (CUDA IPC arenas + descriptor files under KTB_STORE_DIR)."""
+    comp = lambda: kt.Compute(gpus=1).distribute("spmd", workers=1, num_proc=2, devices=[0, 0])  # noqa: E731
+    cls_put = kt.fn(cases.store_put_by_rank, name="t-store")
+    cls_put.to(comp())
+    try:
+        assert cls_put(1000) == [0, 1]
+        # same deployment (same rank processes, same store dir): a second callable would restart the ranks, so reuse
+        # the worker pool through a tiny dispatcher: deploy the getter on the SAME supervisor's store dir
+        store_dir = cls_put._supervisor.env_vars["KTB_STORE_DIR"]
+        getter = kt.fn(cases.store_get_from_rank, name="t-store-get").to(
+            kt.Compute(gpus=1, env_vars={"KTB_STORE_DIR": store_dir}).distribute("spmd", workers=1, num_proc=2,
+                                                                                 devices=[0, 0]))
+        try:
+            out = getter(1, 1000)        # both getter ranks (new processes) read what putter rank 1 published
+            assert [o[0] for o in out] == [1000.0, 1000.0]
+            assert out[0][1] == ["by-rank/0", "by-rank/1"]
+            out0 = getter(0, 1000)
+            assert [o[0] for o in out0] == [0.0, 0.0]
+        finally:
+            getter.teardown()
+    finally:
+        cls_put.teardown()
