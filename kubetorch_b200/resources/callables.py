@@ -196,7 +196,8 @@ class Module:
             return dict(distribution_type="b200", callable_obj=target, num_proc=n, distributed=bool(dist),
                         devices=dist.get("devices") if dist else None,
                         transfer=(dist.get("transfer", "auto") if dist else "auto"),
-                        host_mode=(dist.get("host_mode", "multi") if dist else "multi"), **common)
+                        host_mode=(dist.get("host_mode", "multi") if dist else "multi"),
+                        placement=(dist.get("placement", "ranks") if dist else "ranks"), **common)
         if dtype in SPMD_TYPES:
             extra = {k: v for k, v in dist.items()
                      if k not in ("distribution_type", "workers", "quorum_workers", "num_proc", "port",

@@ -32,7 +32,7 @@ class B200Supervisor:
     def __init__(self, pointers=None, init_args=None, name: str = None, devices: Optional[List[int]] = None,
                  num_proc=None, distributed: bool = True, allowed_serialization: str = "json,pickle",
                  host_chunk_bytes: int = 16 << 20, variant: int = 0, callable_obj=None, transfer: str = "auto",
-                 host_mode: str = "multi", **extra):
+                 host_mode: str = "multi", placement: str = "ranks", **extra):
         self.pointers, self.init_args, self.name = pointers, init_args, name
         self.callable_obj = callable_obj
         self.devices = list(devices) if devices is not None else None
@@ -51,6 +51,12 @@ class B200Supervisor:
             raise ValueError("transfer must be 'auto', 'pull' or 'push'")
         self.transfer = transfer
         self.host_mode = host_mode  # "multi": one C call drives all GPUs; "threads": one host thread per rank
+        # where device-resident element-wise shards execute: "ranks" = rank r on GPU r (the sharded path the
+        # benchmarks measure); "root" = every rank's shard on the root GPU (same results; for HBM-bound ops a
+        # root-resident arg is served faster by the root's own HBM than through its NVLink port, profiles §2)
+        if placement not in ("ranks", "root"):
+            raise ValueError("placement must be 'ranks' or 'root'")
+        self.placement = placement
         self.config_hash = hash(("b200", tuple(self.devices or ()), num_proc, distributed))
 
     # ---- lifecycle ------------------------------------------------------------------------------------
@@ -145,6 +151,10 @@ class B200Supervisor:
         x = x.contiguous()
         with torch.cuda.device(root):
             out = torch.empty_like(x)
+        if self.placement == "root":
+            ops.scatter_map_gather(x, op, alpha, beta, devices=[root] * len(self.devices), out_root=out,
+                                   variant=self.variant)
+            return self._shard_views(out, x)
         distinct = len(set(self.devices)) == len(self.devices) and len(self.devices) > 1
         if self.transfer == "push" or (self.transfer == "auto" and distinct and x.numel() * x.element_size() >= (8 << 20)):
             # push/push flag pipeline: both NVLink directions carry posted writes (see ktb_push.cu)

@@ -333,3 +333,18 @@ def test_kt_put_get_between_rank_processes():
             getter.teardown()
     finally:
         cls_put.teardown()
+
+
+def test_root_placement_option_gives_identical_results():
+    double = _mapped(cases.double, "scale", alpha=2.0)
+    n_dev = torch.cuda.device_count()
+    devices = list(range(min(n_dev, 2))) * (2 if n_dev < 2 else 1)
+    remote = kt.fn(double, name="t-placement").to(
+        kt.Compute(gpus=1).distribute("b200", workers=1, num_proc=len(devices), devices=devices, placement="root"))
+    try:
+        x = torch.randn(10_007)
+        got = remote(x.cuda(0), serialization="pickle")
+        want = ref_dispatch.spmd_call(cases.double, x, num_proc=len(devices), serialization="pickle")
+        assert all(torch.equal(g.cpu(), w) for g, w in zip(got, want))
+    finally:
+        remote.teardown()
