@@ -21,6 +21,7 @@
 
 #include <cuda.h>
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 
 namespace ktb {
@@ -781,7 +782,40 @@ static int get_encoder() {
 }
 
 // Row-major bf16 [rows, cols] matrix, box = [box_rows, 64 cols], 128-byte swizzle.
+static int encode_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+
+// The descriptor depends only on (base, rows, cols, box_rows): weights, scratch and staging repeat every chunk and
+// every call, so each host thread keeps a small cache (the per-rank issue loop is host-bound at 8 GPUs).
 static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  struct Key {
+    const void* base;
+    uint64_t rows, cols;
+    uint32_t box;
+    bool operator==(const Key& o) const { return base == o.base && rows == o.rows && cols == o.cols && box == o.box; }
+  };
+  struct Slot {
+    Key key;
+    CUtensorMap map;
+    bool used = false;
+  };
+  constexpr int kSlots = 64;
+  thread_local Slot cache[kSlots];
+  const Key k{base, rows, cols, box_rows};
+  const size_t h = ((uintptr_t)base >> 8) * 0x9E3779B97F4A7C15ull + rows * 31 + cols * 7 + box_rows;
+  Slot& s = cache[h % kSlots];
+  if (s.used && s.key == k) {
+    *map = s.map;
+    return KTB_OK;
+  }
+  int rc = encode_map(map, base, rows, cols, box_rows);
+  if (rc) return rc;
+  s.key = k;
+  s.map = *map;
+  s.used = true;
+  return KTB_OK;
+}
+
+static int encode_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {cols * 2};
   cuuint32_t box[2] = {(cuuint32_t)kMlpBlockK, box_rows};
@@ -793,8 +827,22 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t 
   return KTB_OK;
 }
 
+// cudaFuncSetAttribute once per (kernel, device) instead of on every launch.
+template <typename KernelT>
+static int ensure_smem_attr(KernelT kfn, int smem_bytes, std::atomic<unsigned>& done_mask, int dev) {
+  if (dev >= 0 && dev < 32 && (done_mask.load(std::memory_order_acquire) & (1u << dev))) return KTB_OK;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(max dynamic shared memory = %d) failed: %s", smem_bytes, cudaGetErrorString(e));
+    return KTB_ERR_CUDA;
+  }
+  if (dev >= 0 && dev < 32) done_mask.fetch_or(1u << dev, std::memory_order_release);
+  return KTB_OK;
+}
+
 template <int BLOCK_N, int STAGES, bool RELU>
-static int launch_gemm(const void* A, const void* B, void* C, size_t M, int N, int K, int ldc, cudaStream_t stream) {
+static int launch_gemm(int dev, const void* A, const void* B, void* C, size_t M, int N, int K, int ldc,
+                       cudaStream_t stream) {
   using S = MlpSmem<BLOCK_N, STAGES>;
   CUtensorMap ma, mb;
   int rc = make_map(&ma, A, M, (uint64_t)K, kMlpBlockM);
@@ -810,17 +858,23 @@ static int launch_gemm(const void* A, const void* B, void* C, size_t M, int N, i
     rc = make_map(&mc, C, M, (uint64_t)N, kMlpBlockM);
     if (rc) return rc;
     const int tiles_m = (int)(M / 256), tiles_n = N / 256;
-    int dev = 0;
-    KTB_CK(cudaGetDevice(&dev));
     const int sms = device_info(dev) ? device_info(dev)->sm_count : 148;
     const int grid = std::max(2, std::min(2 * tiles_m * tiles_n, sms & ~1));
     if (g_mlp_epi_groups == 2) {
       auto kfn = gemm_bf16_tn_2sm_kernel<ST, RELU, 2>;
-      KTB_CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      {
+      static std::atomic<unsigned> attr_done{0};
+      rc = ensure_smem_attr(kfn, smem_bytes, attr_done, dev);
+      if (rc) return rc;
+    }
       kfn<<<grid, 64 + 256, smem_bytes, stream>>>(ma, mb2, mc, K, tiles_m, tiles_n);
     } else {
       auto kfn = gemm_bf16_tn_2sm_kernel<ST, RELU, 1>;
-      KTB_CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      {
+      static std::atomic<unsigned> attr_done{0};
+      rc = ensure_smem_attr(kfn, smem_bytes, attr_done, dev);
+      if (rc) return rc;
+    }
       kfn<<<grid, 64 + 128, smem_bytes, stream>>>(ma, mb2, mc, K, tiles_m, tiles_n);
     }
   } else if (g_mlp_persistent && g_mlp_tma_store && BLOCK_N == 256 && ldc == N) {
@@ -831,31 +885,43 @@ static int launch_gemm(const void* A, const void* B, void* C, size_t M, int N, i
     rc = make_map(&mc, C, M, (uint64_t)N, kMlpBlockM);
     if (rc) return rc;
     auto kfn = gemm_bf16_tn_tmastore_kernel<ST, RELU>;
-    KTB_CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    {
+      static std::atomic<unsigned> attr_done{0};
+      rc = ensure_smem_attr(kfn, smem_bytes, attr_done, dev);
+      if (rc) return rc;
+    }
     const int tiles_m = (int)(M / kMlpBlockM), tiles_n = N / 256;
-    int dev = 0;
-    KTB_CK(cudaGetDevice(&dev));
     const int sms = device_info(dev) ? device_info(dev)->sm_count : 148;
     const int grid = std::min(tiles_m * tiles_n, sms);
     kfn<<<grid, kMlpThreads, smem_bytes, stream>>>(ma, mb, mc, K, tiles_m, tiles_n);
   } else if (g_mlp_persistent) {
     const int tiles_m = (int)(M / kMlpBlockM), tiles_n = N / BLOCK_N;
-    int dev = 0;
-    KTB_CK(cudaGetDevice(&dev));
     const int sms = device_info(dev) ? device_info(dev)->sm_count : 148;
     const int grid = std::min(tiles_m * tiles_n, sms);
     if (g_mlp_epi_groups == 2) {
       auto kfn = gemm_bf16_tn_persistent_kernel<BLOCK_N, STAGES, RELU, 2>;
-      KTB_CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+      {
+      static std::atomic<unsigned> attr_done{0};
+      rc = ensure_smem_attr(kfn, S::kTotal, attr_done, dev);
+      if (rc) return rc;
+    }
       kfn<<<grid, 64 + 256, S::kTotal, stream>>>(ma, mb, static_cast<__nv_bfloat16*>(C), ldc, K, tiles_m, tiles_n);
     } else {
       auto kfn = gemm_bf16_tn_persistent_kernel<BLOCK_N, STAGES, RELU, 1>;
-      KTB_CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+      {
+      static std::atomic<unsigned> attr_done{0};
+      rc = ensure_smem_attr(kfn, S::kTotal, attr_done, dev);
+      if (rc) return rc;
+    }
       kfn<<<grid, 64 + 128, S::kTotal, stream>>>(ma, mb, static_cast<__nv_bfloat16*>(C), ldc, K, tiles_m, tiles_n);
     }
   } else {
     auto kfn = gemm_bf16_tn_kernel<BLOCK_N, STAGES, RELU>;
-    KTB_CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    {
+      static std::atomic<unsigned> attr_done{0};
+      rc = ensure_smem_attr(kfn, S::kTotal, attr_done, dev);
+      if (rc) return rc;
+    }
     dim3 grid((unsigned)(M / kMlpBlockM), (unsigned)(N / BLOCK_N));
     kfn<<<grid, kMlpThreads, S::kTotal, stream>>>(ma, mb, static_cast<__nv_bfloat16*>(C), ldc, K);
   }
@@ -941,12 +1007,12 @@ static int mlp_run(int dev, const void* obs, size_t M, int d_in, int d_hidden, i
       KTB_CK(cudaStreamWaitEvent(st, evs[1 + b], 0));
       a1 = dstb;
     }
-    rc = launch_gemm<256, 4, true>(a1, W1, h1, rows, d_hidden, d_in, d_hidden, st);
+    rc = launch_gemm<256, 4, true>(dev, a1, W1, h1, rows, d_hidden, d_in, d_hidden, st);
     if (rc) return rc;
     if (stg) KTB_CK(cudaEventRecord(evs[3 + (int)(c & 1)], st));
-    rc = launch_gemm<256, 4, true>(h1, W2, h2, rows, d_hidden, d_hidden, d_hidden, st);
+    rc = launch_gemm<256, 4, true>(dev, h1, W2, h2, rows, d_hidden, d_hidden, d_hidden, st);
     if (rc) return rc;
-    rc = launch_gemm<64, 4, false>(h2, W3, y + r0 * d_out, rows, d_out, d_hidden, d_out, st);
+    rc = launch_gemm<64, 4, false>(dev, h2, W3, y + r0 * d_out, rows, d_out, d_hidden, d_out, st);
     if (rc) return rc;
   }
   return KTB_OK;
