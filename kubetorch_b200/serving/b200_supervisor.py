@@ -25,6 +25,7 @@ from typing import List, Optional
 
 from ..mapped import ELEMENTWISE_OPS, mapped_spec
 from .codec import HTTPException, check_allowed
+from .supervisors import check_callable_name
 from .process_worker import instantiate, load_callable, resolve_method
 
 
@@ -102,6 +103,7 @@ class B200Supervisor:
         serialization = request.headers.get("X-Serialization", "json")
         if self._callable is None:
             raise HTTPException(503, "Server is loading the callable. Please retry in a moment.")
+        check_callable_name(cls_or_fn_name, self.name)
         check_allowed(serialization, self.allowed_serialization)
         params = params or {}
         method = resolve_method(self._callable, cls_or_fn_name, method_name)

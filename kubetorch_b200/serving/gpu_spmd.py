@@ -22,7 +22,7 @@ from typing import Dict, List, Optional
 
 from .codec import HTTPException, check_allowed
 from .process_pool import ProcessPool
-from .supervisors import SPMDSupervisor, select_worker_nodes
+from .supervisors import SPMDSupervisor, check_callable_name, select_worker_nodes
 from .tensor_wire import collect_refs, join_tensors, split_tensors
 
 
@@ -115,6 +115,7 @@ class GpuSPMDSupervisor(SPMDSupervisor):
         params = params or {}
         if self.pool is None:
             raise HTTPException(503, "Server is loading the callable. Please retry in a moment.")
+        check_callable_name(cls_or_fn_name, self.name)
         check_allowed(serialization, self.allowed_serialization)
         nodes = select_worker_nodes(params.get("workers"), self.worker_ips, self.worker_ips[0])
         if params.get("restart_procs", False):

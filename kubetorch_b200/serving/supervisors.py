@@ -101,6 +101,13 @@ def auto_num_processes(distribution_type: str) -> int:
     return 1
 
 
+def check_callable_name(requested: str, configured: str) -> None:
+    """run_callable's guard (kt/serving/http_server.py:1741-1750): the endpoint must name the deployed callable."""
+    if configured and requested != configured:
+        raise HTTPException(
+            404, f"Callable '{requested}' not found in metadata configuration. Found '{configured}' instead")
+
+
 class ExecutionSupervisor:
     """Non-distributed execution, in-process (BASELINE config C1: "local in-process backend").
 
@@ -141,6 +148,7 @@ class ExecutionSupervisor:
         serialization = request.headers.get("X-Serialization", "json")
         if self._callable is None:
             raise HTTPException(503, "Server is loading the callable. Please retry in a moment.")
+        check_callable_name(cls_or_fn_name, self.name)
         check_allowed(serialization, self.allowed_serialization)
         params = params or {}
         method = resolve_method(self._callable, cls_or_fn_name, method_name)
@@ -212,6 +220,7 @@ class SPMDSupervisor:
         params = params or {}
         if self.pool is None:
             raise HTTPException(503, "Server is loading the callable. Please retry in a moment.")
+        check_callable_name(cls_or_fn_name, self.name)
         check_allowed(serialization, self.allowed_serialization)
         nodes = select_worker_nodes(params.get("workers"), self.worker_ips, self.worker_ips[0])
         if params.get("restart_procs", False):

@@ -181,17 +181,31 @@ def main():
     env["HOME"] = work
     env["PYTHONDONTWRITEBYTECODE"] = "1"
     all_results = {}
-    only = [a for a in sys.argv[1:] if a in GROUPS]
+    only = [a for a in sys.argv[1:] if a in GROUPS or a == "--helpers-only"]
     if only and os.path.exists(OUT):
         all_results.update(torch.load(OUT, weights_only=False)["cases"])   # keep the other groups' records
-    for group in (only or GROUPS):
+    for group in ([g for g in only if g in GROUPS] if only else GROUPS):
         out_path = os.path.join(work, f"{group}.pkl")
         print(f"[make_golden] {group} ...", flush=True)
         subprocess.run([sys.executable, os.path.abspath(__file__), "--group", group, out_path], env=env, check=True,
                        cwd=work, timeout=600)
         with open(out_path, "rb") as f:
             all_results.update(pickle.load(f))
+    # pure helper of the path: the fan-out tree (no runtime needed; called on the reference class directly)
+    sys.path[:0] = [work, REFERENCE]
+    os.environ.setdefault("KT_LOG_STREAMING_ENABLED", "false")
+    os.environ.setdefault("KT_METRICS_ENABLED", "false")
+    from kubetorch.serving.spmd.spmd_supervisor import SPMDDistributedSupervisor as _RefSup
+
+    tree = []
+    for n, fan in ((1, 50), (7, 2), (120, 50), (300, 50), (1000, 10)):
+        ips = sorted(f"10.0.{i // 250}.{i % 250}" for i in range(n))
+        for who in {ips[0], ips[min(1, n - 1)], ips[n // 2], ips[-1]}:
+            tree.append({"n": n, "fanout": fan, "ip": who,
+                         "children": _RefSup.get_tree_children(None, ips, who, fan)})
+        tree.append({"n": n, "fanout": fan, "ip": "192.168.0.1", "children": _RefSup.get_tree_children(None, ips, "192.168.0.1", fan)})
     fixture = {
+        "tree_children": tree,
         "provenance": {
             "generator": "oracle/make_golden.py",
             "reference": "run-house/kubetorch @ 96fac95 (python_client v0.5.0), unmodified, via fastapi TestClient",

@@ -253,6 +253,26 @@ def select_workers(workers_arg, worker_ips: List[str], this_pod_ip: str) -> Tupl
     return subcall_ips, call_local
 
 
+def tree_children(sorted_ips: List[str], my_ip: str, fanout: int = 100) -> List[str]:
+    """Children of `my_ip` in the self-organising fan-out tree used from 100 pods up
+    (kt/serving/spmd/spmd_supervisor.py:68-101): node i's children are indices [i*F+1, i*F+F]."""
+    if my_ip not in sorted_ips:
+        return []
+    first = sorted_ips.index(my_ip) * fanout + 1
+    if first >= len(sorted_ips):
+        return []
+    return sorted_ips[first:min(first + fanout, len(sorted_ips))]
+
+
+def fanout_targets(worker_ips: List[str], this_ip: str, tree_minimum: int = 100, tree_fanout: int = 50) -> List[str]:
+    """Pods the coordinator (or an inner tree node) calls: everyone else when flat, its tree children otherwise
+    (kt/serving/spmd/spmd_supervisor.py:178-212)."""
+    ips = sorted(worker_ips)
+    if len(ips) < tree_minimum:
+        return [ip for ip in ips if ip != this_ip]
+    return tree_children(ips, this_ip, tree_fanout)
+
+
 # ---- execution (in-process restatement; sequential over ranks) --------------------------------------
 @contextmanager
 def _patched_env(env: Dict[str, str]):

@@ -274,3 +274,17 @@ def test_data_store_surface_without_gpu():
     with pytest.raises(kt.DataStoreError):
         kt.rm("never-put")
     assert kt.ls("never-put") == []
+
+
+def test_endpoint_must_name_the_deployed_callable():
+    from kubetorch_b200.serving.supervisors import Request
+
+    f = kt.fn(cases.summer, name="guard").to(kt.Compute(cpus=1))
+    try:
+        with pytest.raises(Exception, match="Callable 'other' not found in metadata configuration. Found 'summer' instead"):
+            f._supervisor.call(Request({"X-Serialization": "json"}), "other", None, {"args": [1, 2], "kwargs": {}})
+        with pytest.raises(Exception) as ei:
+            f._client().call_method("local://guard/other", body={"args": [1, 2], "kwargs": {}})
+        assert ei.value.status_code == 404
+    finally:
+        f.teardown()

@@ -135,3 +135,16 @@ def test_oracle_runtime_with_real_processes():
     with R.OracleRuntime("oracle.cases", "double", 3, "spmd", extra_path=REPO) as rt:
         out = rt.call(x, serialization="pickle")
     assert [o.numel() for o in out] == [335, 335, 333] and torch.equal(torch.cat(out), x * 2)
+
+
+def test_tree_fanout_matches_reference_outputs(golden):
+    """get_tree_children (spmd_supervisor.py:68-101) restated; vectors produced by calling the reference method."""
+    assert len(golden["tree_children"]) >= 20
+    for rec in golden["tree_children"]:
+        ips = sorted(f"10.0.{i // 250}.{i % 250}" for i in range(rec["n"]))
+        assert R.tree_children(ips, rec["ip"], rec["fanout"]) == rec["children"], rec
+    ips = [f"10.1.0.{i}" for i in range(5)]
+    assert R.fanout_targets(ips, ips[0]) == ips[1:]                      # flat below 100 pods
+    big = sorted(f"10.2.{i // 200}.{i % 200}" for i in range(150))
+    assert R.fanout_targets(big, big[0]) == big[1:51] and R.fanout_targets(big, big[1]) == big[51:101]
+    assert R.fanout_targets(big, big[2]) == big[101:150] and R.fanout_targets(big, big[3]) == []
