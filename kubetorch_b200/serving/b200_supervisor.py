@@ -158,7 +158,11 @@ class B200Supervisor:
                                    variant=self.variant)
             return self._shard_views(out, x)
         distinct = len(set(self.devices)) == len(self.devices) and len(self.devices) > 1
-        if self.transfer == "push" or (self.transfer == "auto" and distinct and x.numel() * x.element_size() >= (8 << 20)):
+        nbytes = x.numel() * x.element_size()
+        # measured crossover (profiles/r1_summary.md §2): the flag pipeline wins from 256 MiB at N >= 4 and from 1 GiB
+        # at N = 2; below that the single fused kernel per rank has less fixed cost
+        auto_push = distinct and ((len(self.devices) >= 4 and nbytes >= (256 << 20)) or nbytes >= (1 << 30))
+        if self.transfer == "push" or (self.transfer == "auto" and auto_push):
             # push/push flag pipeline: both NVLink directions carry posted writes (see ktb_push.cu)
             with self._lock:
                 rows = x.shape[0]
