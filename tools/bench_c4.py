@@ -39,8 +39,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     iters = 10
     e0.record()
+    t_host0 = time.perf_counter()
     for _ in range(iters):
         out = remote(obs, w1, w2, w3, serialization="pickle")
+    host_issue_ms = (time.perf_counter() - t_host0) / iters * 1e3   # time to ENQUEUE one call (no device sync)
     e1.record()
     for d in range(n_gpus):
         torch.cuda.synchronize(d)
@@ -56,7 +58,7 @@ def main():
     flop = 2 * (256 * 1024 + 1024 * 1024 + 1024 * 64) * M
     nbytes = M * 256 * 2 + M * 64 * 2
     print(json.dumps({"what": "c4_rl_rollout", "n_gpus": n_gpus, "ms_per_call": ms, "calls_per_sec": 1e3 / ms,
-                      "arg_plus_result_gbps": nbytes / ms / 1e6, "tflops": flop / ms / 1e9, "parity": "ok (2048 rows)",
+                      "arg_plus_result_gbps": nbytes / ms / 1e6, "tflops": flop / ms / 1e9, "parity": "ok (2048 rows)", "host_issue_ms_per_call": host_issue_ms,
                       "root_nvlink_gbps_each_way": (n_gpus - 1) / n_gpus * (M * 256 * 2) / ms / 1e6 if n_gpus > 1 else 0}),
           flush=True)
     remote.teardown()
