@@ -65,7 +65,8 @@ typedef enum {
   KTB_F32 = 1,
   KTB_BF16 = 2,
   KTB_I32 = 3,           /* wrapping two's-complement arithmetic (torch semantics) */
-  KTB_I64 = 4
+  KTB_I64 = 4,
+  KTB_F16 = 5            /* op-math in fp32, rounded to half (RNE) after each step, like ATen */
 } ktb_dtype;
 
 /* Kernel variant selector for the element-wise map (all bit-identical in output). */

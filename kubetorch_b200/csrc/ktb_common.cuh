@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stddef.h>
 #include <stdio.h>
@@ -86,6 +87,7 @@ inline size_t dtype_size(int dtype) {
     case KTB_BF16: return 2;
     case KTB_I32: return 4;
     case KTB_I64: return 8;
+    case KTB_F16: return 2;
     default: return 0;
   }
 }
@@ -140,6 +142,25 @@ __device__ __forceinline__ uint32_t apply_bf16x2(uint32_t w, const MapParams& p)
   return (__float_as_uint(ylo) >> 16) | (__float_as_uint(yhi) & 0xffff0000u);
 }
 
+__device__ __forceinline__ float f16_round(float x) { return __half2float(__float2half_rn(x)); }
+
+template <int OP>
+__device__ __forceinline__ float apply_f16_as_f32(float x, const MapParams& p) {
+  if constexpr (OP == KTB_OP_IDENTITY) return x;
+  if constexpr (OP == KTB_OP_SCALE) return f16_round(__fmul_rn(x, p.alpha_f));
+  return f16_round(__fadd_rn(f16_round(__fmul_rn(x, p.alpha_f)), p.beta_f));
+}
+
+// Two packed halves in one 32-bit word.
+template <int OP>
+__device__ __forceinline__ uint32_t apply_f16x2(uint32_t w, const MapParams& p) {
+  if constexpr (OP == KTB_OP_IDENTITY) return w;
+  const __half2 h = *reinterpret_cast<const __half2*>(&w);
+  const float2 f = __half22float2(h);
+  const __half2 r = __floats2half2_rn(apply_f16_as_f32<OP>(f.x, p), apply_f16_as_f32<OP>(f.y, p));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
 template <int OP>
 __device__ __forceinline__ uint32_t apply_i32(uint32_t x, const MapParams& p) {
   if constexpr (OP == KTB_OP_IDENTITY) return x;
@@ -165,6 +186,9 @@ __device__ __forceinline__ void apply_words(uint32_t (&w)[NW], const MapParams& 
   } else if constexpr (DT == KTB_BF16) {
 #pragma unroll
     for (int i = 0; i < NW; ++i) w[i] = apply_bf16x2<OP>(w[i], p);
+  } else if constexpr (DT == KTB_F16) {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) w[i] = apply_f16x2<OP>(w[i], p);
   } else if constexpr (DT == KTB_I32) {
 #pragma unroll
     for (int i = 0; i < NW; ++i) w[i] = apply_i32<OP>(w[i], p);
@@ -190,6 +214,9 @@ __device__ __forceinline__ void apply_elem(const uint8_t* src, uint8_t* dst, con
     uint16_t h = *reinterpret_cast<const uint16_t*>(src);
     float y = apply_bf16_as_f32<OP>(__uint_as_float((uint32_t)h << 16), p);
     *reinterpret_cast<uint16_t*>(dst) = (uint16_t)(__float_as_uint(y) >> 16);
+  } else if constexpr (DT == KTB_F16) {
+    const __half h = *reinterpret_cast<const __half*>(src);
+    *reinterpret_cast<__half*>(dst) = __float2half_rn(apply_f16_as_f32<OP>(__half2float(h), p));
   } else if constexpr (DT == KTB_I32) {
     *reinterpret_cast<uint32_t*>(dst) = apply_i32<OP>(*reinterpret_cast<const uint32_t*>(src), p);
   } else {

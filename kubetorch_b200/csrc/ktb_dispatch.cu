@@ -220,7 +220,7 @@ int ktb_scatter_map_reduce(int op, int dtype, const void* src_root, size_t n_ele
   KTB_REQUIRE(granule > 0 && n_elems % granule == 0, KTB_ERR_ARG,
               "ktb_scatter_map_reduce: n_elems %zu is not a multiple of granule %zu", n_elems, granule);
   const MapParams p = make_params(alpha, beta);
-  const size_t acc_size = (dtype == KTB_F32 || dtype == KTB_BF16) ? 4 : 8;
+  const size_t acc_size = (dtype == KTB_F32 || dtype == KTB_BF16 || dtype == KTB_F16) ? 4 : 8;
   const int root_dev = devs[root_rank];
   DeviceInfo* root = device_info(root_dev);
   // streams == NULL → library streams; otherwise streams[r] verbatim (0 is the legacy default stream)

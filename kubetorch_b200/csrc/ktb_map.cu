@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kVecThreads)
       apply_words<DT, OP, NW>(w, p);
       st_vec<VB, FL>(dst + base + v * VB, w);
     }
-    constexpr size_t ES = (DT == KTB_U8) ? 1 : (DT == KTB_BF16 ? 2 : (DT == KTB_I64 ? 8 : 4));
+    constexpr size_t ES = (DT == KTB_U8) ? 1 : ((DT == KTB_BF16 || DT == KTB_F16) ? 2 : (DT == KTB_I64 ? 8 : 4));
     const size_t tail = base + n_vec * VB;
     const size_t n_tail = (n_bytes - tail) / ES;
     for (size_t e = threadIdx.x; e < n_tail; e += kVecThreads)
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kVecThreads)
 template <int DT, int OP>
 __global__ void __launch_bounds__(256)
     map_scalar_kernel(const uint8_t* src, uint8_t* dst, size_t n_elems, MapParams p) {
-  constexpr size_t ES = (DT == KTB_U8) ? 1 : (DT == KTB_BF16 ? 2 : (DT == KTB_I64 ? 8 : 4));
+  constexpr size_t ES = (DT == KTB_U8) ? 1 : ((DT == KTB_BF16 || DT == KTB_F16) ? 2 : (DT == KTB_I64 ? 8 : 4));
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += stride)
     apply_elem<DT, OP>(src + i * ES, dst + i * ES, p);
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(NT)
 
   // < 16 trailing bytes: element tail by CTA 0.
   if (blockIdx.x == 0) {
-    constexpr size_t ES = (DT == KTB_U8) ? 1 : (DT == KTB_BF16 ? 2 : (DT == KTB_I64 ? 8 : 4));
+    constexpr size_t ES = (DT == KTB_U8) ? 1 : ((DT == KTB_BF16 || DT == KTB_F16) ? 2 : (DT == KTB_I64 ? 8 : 4));
     const size_t n_tail = (n_bytes - n16) / ES;
     for (size_t e = threadIdx.x; e < n_tail; e += NT)
       apply_elem<DT, OP>(src + n16 + e * ES, dst + n16 + e * ES, p);
@@ -335,6 +335,7 @@ int launch_map(int dev, int op, int dtype, const void* src_, void* dst_, size_t 
     KTB_CASE(KTB_BF16)
     KTB_CASE(KTB_I32)
     KTB_CASE(KTB_I64)
+    KTB_CASE(KTB_F16)
   }
 #undef KTB_CASE
   set_error("ktb_map: unsupported dtype/op %d/%d", dtype, op);

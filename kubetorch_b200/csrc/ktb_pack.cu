@@ -33,7 +33,7 @@ struct SegBatch {
 
 template <int DT, int OP>
 __global__ void __launch_bounds__(kSegThreads) seg_map_kernel(const __grid_constant__ SegBatch b, MapParams p) {
-  constexpr size_t ES = (DT == KTB_U8) ? 1 : (DT == KTB_BF16 ? 2 : (DT == KTB_I64 ? 8 : 4));
+  constexpr size_t ES = (DT == KTB_U8) ? 1 : ((DT == KTB_BF16 || DT == KTB_F16) ? 2 : (DT == KTB_I64 ? 8 : 4));
   const uint32_t n_tiles = b.tile_prefix[b.n];
   for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     // binary search: largest i with tile_prefix[i] <= t
@@ -123,6 +123,7 @@ static int launch_seg(int dev, int op, int dtype, const SegBatch& b, const MapPa
     KTB_SCASE(KTB_BF16)
     KTB_SCASE(KTB_I32)
     KTB_SCASE(KTB_I64)
+    KTB_SCASE(KTB_F16)
   }
 #undef KTB_SCASE
   set_error("ktb_map_batch: unsupported dtype/op %d/%d", dtype, op);

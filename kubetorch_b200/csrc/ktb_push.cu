@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kPushThreads)
     push_consume_kernel(const uint8_t* stage, uint8_t* dst, size_t n_bytes, MapParams p,
                         const unsigned long long* ready, unsigned long long seq, unsigned long long* ack,
                         int publish_ack, unsigned int* ticket, unsigned int* status) {
-  constexpr size_t ES = (DT == KTB_U8) ? 1 : (DT == KTB_BF16 ? 2 : (DT == KTB_I64 ? 8 : 4));
+  constexpr size_t ES = (DT == KTB_U8) ? 1 : ((DT == KTB_BF16 || DT == KTB_F16) ? 2 : (DT == KTB_I64 ? 8 : 4));
   __shared__ bool flag;
   if (threadIdx.x == 0) flag = spin_until(ready, seq, status);
   __syncthreads();
@@ -299,6 +299,7 @@ int ktb_push_consume(int dev, int op, int dtype, const void* stage_local, size_t
         case KTB_F32: if (op == KTB_OP_SCALE) KTB_PC(KTB_F32, KTB_OP_SCALE); else KTB_PC(KTB_F32, KTB_OP_AFFINE); break;
         case KTB_BF16: if (op == KTB_OP_SCALE) KTB_PC(KTB_BF16, KTB_OP_SCALE); else KTB_PC(KTB_BF16, KTB_OP_AFFINE); break;
         case KTB_I32: if (op == KTB_OP_SCALE) KTB_PC(KTB_I32, KTB_OP_SCALE); else KTB_PC(KTB_I32, KTB_OP_AFFINE); break;
+        case KTB_F16: if (op == KTB_OP_SCALE) KTB_PC(KTB_F16, KTB_OP_SCALE); else KTB_PC(KTB_F16, KTB_OP_AFFINE); break;
         default: if (op == KTB_OP_SCALE) KTB_PC(KTB_I64, KTB_OP_SCALE); else KTB_PC(KTB_I64, KTB_OP_AFFINE); break;
       }
     }

@@ -38,6 +38,8 @@ __device__ __forceinline__ typename Acc<DT>::type elem_value(const uint8_t* p, c
   } else if constexpr (DT == KTB_BF16) {
     uint16_t h = *reinterpret_cast<const uint16_t*>(p);
     return apply_bf16_as_f32<OP>(__uint_as_float((uint32_t)h << 16), mp);
+  } else if constexpr (DT == KTB_F16) {
+    return apply_f16_as_f32<OP>(__half2float(*reinterpret_cast<const __half*>(p)), mp);
   } else if constexpr (DT == KTB_I32) {
     return (long long)(int)apply_i32<OP>(*reinterpret_cast<const uint32_t*>(p), mp);
   } else {
@@ -59,6 +61,15 @@ __device__ __forceinline__ typename Acc<DT>::type words_value(const uint32_t (&w
     for (int i = 0; i < NW; ++i) {
       s += apply_bf16_as_f32<OP>(__uint_as_float(w[i] << 16), mp);
       s += apply_bf16_as_f32<OP>(__uint_as_float(w[i] & 0xffff0000u), mp);
+    }
+    return s;
+  } else if constexpr (DT == KTB_F16) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      s += apply_f16_as_f32<OP>(f.x, mp);
+      s += apply_f16_as_f32<OP>(f.y, mp);
     }
     return s;
   } else if constexpr (DT == KTB_I32) {
@@ -104,7 +115,7 @@ __global__ void __launch_bounds__(kRedThreads)
   using A = typename Acc<DT>::type;
   // cross-CTA partials are kept in fp64 for float sums, int64 for integer sums
   using P = typename std::conditional<std::is_same<A, float>::value, double, long long>::type;
-  constexpr size_t ES = (DT == KTB_BF16) ? 2 : (DT == KTB_I64 ? 8 : 4);
+  constexpr size_t ES = (DT == KTB_BF16 || DT == KTB_F16) ? 2 : (DT == KTB_I64 ? 8 : 4);
   __shared__ P red[32];
   __shared__ bool is_last;
 
@@ -182,7 +193,7 @@ static int launch_reduce_typed(int dev, const uint8_t* src, size_t n_elems, cons
                                void* out, void* ws, cudaStream_t stream) {
   const DeviceInfo* di = device_info(dev);
   (void)di;
-  constexpr size_t ES = (DT == KTB_BF16) ? 2 : (DT == KTB_I64 ? 8 : 4);
+  constexpr size_t ES = (DT == KTB_BF16 || DT == KTB_F16) ? 2 : (DT == KTB_I64 ? 8 : 4);
   const size_t tiles = (n_elems * ES + 32767) / 32768;   // one 32 KiB tile per CTA
   const size_t cap = g_red_ctas_per_sm > 0 ? std::min<size_t>((size_t)kRedMaxGrid, (size_t)g_red_ctas_per_sm * 1024) : kRedMaxGrid;
   int grid = (int)std::min<size_t>(std::max<size_t>(tiles, 1), cap);
@@ -193,7 +204,7 @@ static int launch_reduce_typed(int dev, const uint8_t* src, size_t n_elems, cons
 
 int launch_map_reduce(int dev, int op, int dtype, const void* src, size_t n_elems, const MapParams& p,
                       void* out, void* workspace, cudaStream_t stream) {
-  KTB_REQUIRE(dtype == KTB_F32 || dtype == KTB_BF16 || dtype == KTB_I32 || dtype == KTB_I64, KTB_ERR_ARG,
+  KTB_REQUIRE(dtype == KTB_F32 || dtype == KTB_BF16 || dtype == KTB_F16 || dtype == KTB_I32 || dtype == KTB_I64, KTB_ERR_ARG,
               "ktb_map_reduce_sum: dtype %d not reducible", dtype);
   KTB_REQUIRE(op >= KTB_OP_IDENTITY && op <= KTB_OP_AFFINE, KTB_ERR_ARG, "ktb_map_reduce_sum: unknown op %d", op);
   KTB_REQUIRE(out && workspace, KTB_ERR_ARG, "ktb_map_reduce_sum: null out/workspace");
@@ -216,6 +227,7 @@ int launch_map_reduce(int dev, int op, int dtype, const void* src, size_t n_elem
     KTB_RCASE(KTB_BF16)
     KTB_RCASE(KTB_I32)
     KTB_RCASE(KTB_I64)
+    KTB_RCASE(KTB_F16)
   }
 #undef KTB_RCASE
   return KTB_ERR_UNSUPPORTED;
@@ -224,7 +236,7 @@ int launch_map_reduce(int dev, int op, int dtype, const void* src, size_t n_elem
 int launch_reduce_partials(int dev, int dtype, const void* partials, int n, void* out, cudaStream_t stream) {
   (void)dev;
   KTB_REQUIRE(partials && out && n > 0, KTB_ERR_ARG, "ktb_reduce_partials: bad arguments");
-  if (dtype == KTB_F32 || dtype == KTB_BF16)
+  if (dtype == KTB_F32 || dtype == KTB_BF16 || dtype == KTB_F16)
     reduce_partials_kernel<float, double><<<1, kRedThreads, 0, stream>>>((const float*)partials, n, (float*)out);
   else if (dtype == KTB_I32 || dtype == KTB_I64)
     reduce_partials_kernel<long long, long long>

@@ -15,7 +15,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file_
 
 # enums (include/ktb200.h)
 OP_IDENTITY, OP_SCALE, OP_AFFINE = 0, 1, 2
-U8, F32, BF16, I32, I64 = 0, 1, 2, 3, 4
+U8, F32, BF16, I32, I64, F16 = 0, 1, 2, 3, 4, 5
 VARIANT_AUTO, VARIANT_VEC, VARIANT_TMA, VARIANT_SCALAR = 0, 1, 2, 3
 OK, ERR_CUDA, ERR_ARG, ERR_STATE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 PACK_ALIGN = 256

@@ -21,6 +21,7 @@ _DTYPE_CODES = {
     torch.bfloat16: L.BF16,
     torch.int32: L.I32,
     torch.int64: L.I64,
+    torch.float16: L.F16,
 }
 OPS = {"identity": L.OP_IDENTITY, "scale": L.OP_SCALE, "affine": L.OP_AFFINE}
 
@@ -134,7 +135,7 @@ def _workspace(dev: int) -> torch.Tensor:
 
 
 def acc_dtype(dtype: torch.dtype) -> torch.dtype:
-    return torch.float32 if dtype in (torch.float32, torch.bfloat16) else torch.int64
+    return torch.float32 if dtype in (torch.float32, torch.bfloat16, torch.float16) else torch.int64
 
 
 def map_reduce_sum(

@@ -26,6 +26,7 @@ def make_inputs():
         "i32_515": torch.randint(-(2**31), 2**31 - 1, (515,), dtype=torch.int32, generator=g),
         "i64_130": torch.randint(-(2**40), 2**40, (130,), dtype=torch.int64, generator=g),
         "f32_3": torch.tensor([1.0, 2.0, 3.0]),
+        "f16_515": (torch.randn(515, generator=torch.Generator().manual_seed(16)) * 8).half(),
         "mlp_obs": torch.randn(256, d_in, generator=g).bfloat16(),
         "mlp_w1": (torch.randn(d_h, d_in, generator=g) * 0.02).bfloat16(),
         "mlp_w2": (torch.randn(d_h, d_h, generator=g) * 0.02).bfloat16(),

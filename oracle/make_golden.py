@@ -85,6 +85,9 @@ GROUPS = {
         ("affine_i32_515_x2", None, ["@i32_515", 3, -7], {}, "pickle"),
         ("affine_i64_130_x2", None, ["@i64_130", -5, 11], {}, "pickle"),
     ]),
+    "affine_f16_spmd3": ("affine", {"distribution_type": "spmd", "num_proc": 3}, "json,pickle", [
+        ("affine_f16_515_x3", None, ["@f16_515", 1.7, -0.3], {}, "pickle"),
+    ]),
     "scale_spmd4": ("scale", {"distribution_type": "spmd", "num_proc": 4}, "json,pickle", [
         ("scale_f32_1001_x4", None, ["@f32_rand_1001", 0.1], {}, "pickle"),
         ("scale_i32_515_x4", None, ["@i32_515", 65537], {}, "pickle"),  # wraps

@@ -30,6 +30,8 @@ def _rand(dtype, n, seed=0):
         return torch.randn(n, generator=g)
     if dtype == torch.bfloat16:
         return torch.randn(n, generator=g).bfloat16()
+    if dtype == torch.float16:
+        return (torch.randn(n, generator=g) * 8).half()
     if dtype == torch.uint8:
         return torch.randint(0, 256, (n,), dtype=torch.uint8, generator=g)
     if dtype == torch.int32:
@@ -59,6 +61,9 @@ VARIANTS = [1, 2, 3]  # VEC, TMA, SCALAR
     (torch.bfloat16, "scale", 2.0, 0),
     (torch.bfloat16, "scale", 1.7, 0),
     (torch.bfloat16, "affine", 1.5, 0.25),
+    (torch.float16, "scale", 1.7, 0),
+    (torch.float16, "affine", 1.5, 0.25),
+    (torch.float16, "identity", 1, 0),
     (torch.int32, "scale", 65537, 0),
     (torch.int32, "affine", 3, -7),
     (torch.int64, "scale", -5, 0),
@@ -149,7 +154,7 @@ def test_golden_sums(K, golden):
             assert int(total.item()) == sum(rec["result"])
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.int32, torch.int64])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16, torch.int32, torch.int64])
 def test_reduce_sizes(K, dtype):
     for n in [0, 1, 33, 1000, 70_001, (1 << 21) + 5]:
         x = _rand(dtype, n, seed=n + 1)
