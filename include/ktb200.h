@@ -57,7 +57,8 @@ typedef enum {
 typedef enum {
   KTB_OP_IDENTITY = 0,   /* y = x                         (BASELINE config C5)       */
   KTB_OP_SCALE = 1,      /* y = x * alpha                 (BASELINE config C2: x→2x) */
-  KTB_OP_AFFINE = 2      /* y = (x * alpha) + beta, each step rounded to dtype        */
+  KTB_OP_AFFINE = 2      /* y = (x * alpha) + beta, each step rounded to dtype; for BF16/F16 beta is
+                          * itself rounded to the dtype first (torch CPU eager scalar semantics)  */
 } ktb_op;
 
 typedef enum {

@@ -97,10 +97,15 @@ struct MapParams {
   float alpha_f, beta_f;
   long long alpha_i, beta_i;
 };
-inline MapParams make_params(double alpha, double beta) {
+// alpha/beta → op-math parameters with the reference's (torch CPU eager) scalar semantics, measured against the
+// reference runtime's recorded results: `x * alpha` keeps alpha in fp32 for bf16/fp16 tensors, but `+ beta` wraps
+// the scalar in a tensor of the RESULT dtype first, i.e. beta is rounded to bf16/fp16 before the fp32 add.
+inline MapParams make_params(double alpha, double beta, int dtype = KTB_F32) {
   MapParams p;
   p.alpha_f = (float)alpha;
   p.beta_f = (float)beta;
+  if (dtype == KTB_BF16) p.beta_f = __bfloat162float(__float2bfloat16_rn(p.beta_f));
+  if (dtype == KTB_F16) p.beta_f = __half2float(__float2half_rn(p.beta_f));
   p.alpha_i = (long long)alpha;
   p.beta_i = (long long)beta;
   return p;

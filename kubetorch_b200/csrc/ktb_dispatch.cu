@@ -158,7 +158,7 @@ int ktb_scatter_map_gather(int op, int dtype, const void* src_root, void* dst_ro
   KTB_REQUIRE(src_root && dst_root, KTB_ERR_ARG, "ktb_scatter_map_gather: null src/dst");
   KTB_REQUIRE(granule > 0 && n_elems % granule == 0, KTB_ERR_ARG,
               "ktb_scatter_map_gather: n_elems %zu is not a multiple of granule %zu", n_elems, granule);
-  const MapParams p = make_params(alpha, beta);
+  const MapParams p = make_params(alpha, beta, dtype);
   const int root_dev = devs[root_rank];
   DeviceInfo* root = device_info(root_dev);
   // streams == NULL → library streams; otherwise streams[r] verbatim (0 is the legacy default stream)
@@ -219,7 +219,7 @@ int ktb_scatter_map_reduce(int op, int dtype, const void* src_root, size_t n_ele
   KTB_REQUIRE(src_root || n_elems == 0, KTB_ERR_ARG, "ktb_scatter_map_reduce: null src");
   KTB_REQUIRE(granule > 0 && n_elems % granule == 0, KTB_ERR_ARG,
               "ktb_scatter_map_reduce: n_elems %zu is not a multiple of granule %zu", n_elems, granule);
-  const MapParams p = make_params(alpha, beta);
+  const MapParams p = make_params(alpha, beta, dtype);
   const size_t acc_size = (dtype == KTB_F32 || dtype == KTB_BF16 || dtype == KTB_F16) ? 4 : 8;
   const int root_dev = devs[root_rank];
   DeviceInfo* root = device_info(root_dev);
@@ -278,7 +278,7 @@ int ktb_map_host(int dev, int op, int dtype, const void* src_host, void* dst_hos
               "ktb_map_host: chunk_bytes must be a multiple of 256 and >= 4096 (got %zu)", chunk_bytes);
   KTB_GUARD(dev);
   DeviceInfo* di = device_info(dev);
-  const MapParams p = make_params(alpha, beta);
+  const MapParams p = make_params(alpha, beta, dtype);
   const size_t n_bytes = n_elems * es;
   const size_t n_chunks = (n_bytes + chunk_bytes - 1) / chunk_bytes;
   cudaEvent_t h2d_done[2], exec_done[2], d2h_done[2];
@@ -354,7 +354,7 @@ int ktb_map_host_multi(int op, int dtype, const void* src_host, void* dst_host, 
   }
   static std::mutex host_multi_mu;   // the per-device copy/exec streams and events carry one call at a time
   std::lock_guard<std::mutex> lk(host_multi_mu);
-  const MapParams p = make_params(alpha, beta);
+  const MapParams p = make_params(alpha, beta, dtype);
   size_t sb[kMaxDevices], sbytes[kMaxDevices], max_chunks = 0;
   for (int r = 0; r < n_ranks; ++r) {
     size_t b = 0, e = 0;

@@ -381,7 +381,7 @@ int ktb_map(int dev, int op, int dtype, const void* src, void* dst, size_t n_ele
   int rc = require_device(dev);
   if (rc) return rc;
   KTB_GUARD(dev);
-  return launch_map(dev, op, dtype, src, dst, n_elems, make_params(alpha, beta), variant,
+  return launch_map(dev, op, dtype, src, dst, n_elems, make_params(alpha, beta, dtype), variant,
                     reinterpret_cast<cudaStream_t>(stream));
 }
 

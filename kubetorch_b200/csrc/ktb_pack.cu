@@ -231,7 +231,7 @@ int ktb_map_batch(int dev, int op, int dtype, const void* const* srcs, void* con
   std::vector<size_t> nb((size_t)n);
   for (int i = 0; i < n; ++i) nb[(size_t)i] = n_elems[i] * es;
   KTB_GUARD(dev);
-  return run_segments(dev, op, dtype, srcs, dsts, nb.data(), n, make_params(alpha, beta),
+  return run_segments(dev, op, dtype, srcs, dsts, nb.data(), n, make_params(alpha, beta, dtype),
                       reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -274,7 +274,7 @@ int ktb_push_consume(int dev, int op, int dtype, const void* stage_local, size_t
               "ktb_push_consume: null argument");
   KTB_GUARD(dev);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const MapParams p = make_params(alpha, beta);
+  const MapParams p = make_params(alpha, beta, dtype);
   uint8_t* cl = static_cast<uint8_t*>(ctrl_local);
   const unsigned long long* ready = reinterpret_cast<const unsigned long long*>(cl + KTB_CTRL_READY);
   unsigned int* ticket = reinterpret_cast<unsigned int*>(cl + KTB_CTRL_TICKET);

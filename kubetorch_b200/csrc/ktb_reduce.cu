@@ -262,7 +262,7 @@ int ktb_map_reduce_sum(int dev, int op, int dtype, const void* src, size_t n_ele
   int rc = require_device(dev);
   if (rc) return rc;
   KTB_GUARD(dev);
-  return launch_map_reduce(dev, op, dtype, src, n_elems, make_params(alpha, beta), out, workspace,
+  return launch_map_reduce(dev, op, dtype, src, n_elems, make_params(alpha, beta, dtype), out, workspace,
                            reinterpret_cast<cudaStream_t>(stream));
 }
 

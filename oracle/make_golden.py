@@ -81,6 +81,7 @@ GROUPS = {
     ]),
     "affine_spmd2": ("affine", {"distribution_type": "spmd", "num_proc": 2}, "json,pickle", [
         ("affine_bf16_777_x2", None, ["@bf16_777", 1.5, 0.25], {}, "pickle"),
+        ("affine_bf16_777_x2_inexact_scalars", None, ["@bf16_777", 1.7, -0.3], {}, "pickle"),
         ("affine_f32_1001_x2", None, ["@f32_rand_1001", 0.1, 0.3], {}, "pickle"),
         ("affine_i32_515_x2", None, ["@i32_515", 3, -7], {}, "pickle"),
         ("affine_i64_130_x2", None, ["@i64_130", -5, 11], {}, "pickle"),

@@ -61,8 +61,10 @@ VARIANTS = [1, 2, 3]  # VEC, TMA, SCALAR
     (torch.bfloat16, "scale", 2.0, 0),
     (torch.bfloat16, "scale", 1.7, 0),
     (torch.bfloat16, "affine", 1.5, 0.25),
+    (torch.bfloat16, "affine", 1.7, -0.3),   # beta is rounded to bf16 before the add (torch CPU scalar semantics)
     (torch.float16, "scale", 1.7, 0),
     (torch.float16, "affine", 1.5, 0.25),
+    (torch.float16, "affine", 1.7, -0.3),
     (torch.float16, "identity", 1, 0),
     (torch.int32, "scale", 65537, 0),
     (torch.int32, "affine", 3, -7),
