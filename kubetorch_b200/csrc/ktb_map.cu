@@ -20,6 +20,9 @@
 namespace ktb {
 
 extern int g_red_ctas_per_sm;  // ktb_reduce.cu
+extern int g_red_loads;        // ktb_reduce.cu
+extern int g_red_fold;         // ktb_reduce.cu
+extern int g_seg_large;        // ktb_pack.cu
 extern int g_mlp_persistent;   // ktb_mlp.cu
 extern int g_mlp_chunk_rows;   // ktb_mlp.cu
 extern int g_mlp_epi_groups;   // ktb_mlp.cu
@@ -358,11 +361,14 @@ int ktb_set_tuning(int key, int value) {
     case 2: g_tma_cfg = value; return KTB_OK;
     case 4: g_vec_flavor = value; return KTB_OK;
     case 5: g_vec_unroll = value; return KTB_OK;
-    case 6: g_red_ctas_per_sm = value > 0 ? value : 8; return KTB_OK;
+    case 6: g_red_ctas_per_sm = value > 0 ? value : 4; return KTB_OK;
     case 7: g_mlp_persistent = value ? 1 : 0; return KTB_OK;
     case 9: g_mlp_epi_groups = (value == 2) ? 2 : 1; return KTB_OK;
     case 10: g_mlp_tma_store = value ? 1 : 0; return KTB_OK;
     case 11: g_mlp_2sm = value ? 1 : 0; return KTB_OK;
+    case 12: g_seg_large = value ? 1 : 0; return KTB_OK;
+    case 13: g_red_loads = value == 4 ? 4 : 8; return KTB_OK;
+    case 14: g_red_fold = value ? 1 : 0; return KTB_OK;
     case 8:
       KTB_REQUIRE(value > 0 && value % 128 == 0, KTB_ERR_ARG, "ktb_set_tuning: MLP chunk rows must be a multiple of 128");
       g_mlp_chunk_rows = value;

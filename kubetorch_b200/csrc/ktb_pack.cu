@@ -8,31 +8,40 @@
 // Tensor leaves never leave HBM: they are gathered into an arena at KTB_PACK_ALIGN-aligned
 // offsets by one segmented kernel; the (tiny) offset table travels on the host.
 //
-// HBM-bound: algorithmic bytes = 2 * sum(nbytes).  A launch carries up to kSegMax segment
-// descriptors *in the kernel parameters* (no descriptor upload, graph-capturable); work is split
-// into fixed-size tiles across segments so one huge tensor and a thousand tiny ones both fill
-// the machine.
+// HBM-bound: algorithmic bytes = 2 * sum(nbytes).  A launch carries its segment descriptors
+// *in the kernel parameters* (no descriptor upload, graph-capturable): up to kSegSmall in the
+// classic 4 KiB parameter space, up to kSegLarge (28 KiB of parameters, CUDA >= 12.1 large
+// kernel parameters) when a call has more, so 1024 shards still go out as ONE launch.  Work is
+// split into fixed-size tiles across segments so one huge tensor and a thousand tiny ones both
+// fill the machine.
 #include "ktb_common.cuh"
 
 #include <algorithm>
+#include <memory>
 #include <vector>
 
 namespace ktb {
 
-constexpr int kSegMax = 96;               // descriptors per launch (fits the 4 KiB param space)
+constexpr int kSegSmall = 96;             // descriptors per launch in the 4 KiB parameter space
+constexpr int kSegLarge = 1024;           // descriptors per launch with large kernel parameters (< 32764 B)
 constexpr int kSegThreads = 256;
 constexpr uint32_t kSegTile = 32768;      // bytes per CTA work item
+int g_seg_large = 1;                      // ktb_set_tuning key 12: 0 = always kSegSmall descriptors per launch
 
+template <int CAP>
 struct SegBatch {
-  const uint8_t* src[kSegMax];
-  uint8_t* dst[kSegMax];
-  unsigned long long nbytes[kSegMax];
-  uint32_t tile_prefix[kSegMax + 1];      // tile_prefix[i] = first tile id of segment i
+  const uint8_t* src[CAP];
+  uint8_t* dst[CAP];
+  unsigned long long nbytes[CAP];
+  uint32_t tile_prefix[CAP + 1];          // tile_prefix[i] = first tile id of segment i
   int n;
 };
+static_assert(sizeof(SegBatch<kSegSmall>) + sizeof(MapParams) <= 4096, "small batch must fit the classic param space");
+static_assert(sizeof(SegBatch<kSegLarge>) + sizeof(MapParams) <= 32764, "large batch must fit CUDA 12.1+ param space");
 
-template <int DT, int OP>
-__global__ void __launch_bounds__(kSegThreads) seg_map_kernel(const __grid_constant__ SegBatch b, MapParams p) {
+template <int DT, int OP, int CAP>
+__global__ void __launch_bounds__(kSegThreads)
+    seg_map_kernel(const __grid_constant__ SegBatch<CAP> b, const __grid_constant__ MapParams p) {
   constexpr size_t ES = (DT == KTB_U8) ? 1 : ((DT == KTB_BF16 || DT == KTB_F16) ? 2 : (DT == KTB_I64 ? 8 : 4));
   const uint32_t n_tiles = b.tile_prefix[b.n];
   for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -100,24 +109,23 @@ __global__ void __launch_bounds__(kSegThreads) seg_map_kernel(const __grid_const
   }
 }
 
-template <int DT, int OP>
-static int launch_seg_typed(int dev, const SegBatch& b, const MapParams& p, cudaStream_t stream) {
-  const DeviceInfo* di = device_info(dev);
+template <int DT, int OP, int CAP>
+static int launch_seg_typed(const SegBatch<CAP>& b, const MapParams& p, cudaStream_t stream) {
   const uint32_t n_tiles = b.tile_prefix[b.n];
   if (n_tiles == 0) return KTB_OK;
-  (void)di;
   int grid = (int)n_tiles;  // one 32 KiB tile per CTA: the hardware scheduler balances ragged segments
-  seg_map_kernel<DT, OP><<<grid, kSegThreads, 0, stream>>>(b, p);
+  seg_map_kernel<DT, OP, CAP><<<grid, kSegThreads, 0, stream>>>(b, p);
   KTB_CK(cudaGetLastError());
   return KTB_OK;
 }
 
-static int launch_seg(int dev, int op, int dtype, const SegBatch& b, const MapParams& p, cudaStream_t stream) {
-  if (op == KTB_OP_IDENTITY) return launch_seg_typed<KTB_U8, KTB_OP_IDENTITY>(dev, b, p, stream);
-#define KTB_SCASE(DT)                                                              \
-  case DT:                                                                         \
-    return (op == KTB_OP_SCALE) ? launch_seg_typed<DT, KTB_OP_SCALE>(dev, b, p, stream) \
-                                : launch_seg_typed<DT, KTB_OP_AFFINE>(dev, b, p, stream);
+template <int CAP>
+static int launch_seg(int op, int dtype, const SegBatch<CAP>& b, const MapParams& p, cudaStream_t stream) {
+  if (op == KTB_OP_IDENTITY) return launch_seg_typed<KTB_U8, KTB_OP_IDENTITY, CAP>(b, p, stream);
+#define KTB_SCASE(DT)                                                                    \
+  case DT:                                                                               \
+    return (op == KTB_OP_SCALE) ? launch_seg_typed<DT, KTB_OP_SCALE, CAP>(b, p, stream)  \
+                                : launch_seg_typed<DT, KTB_OP_AFFINE, CAP>(b, p, stream);
   switch (dtype) {
     KTB_SCASE(KTB_F32)
     KTB_SCASE(KTB_BF16)
@@ -130,11 +138,11 @@ static int launch_seg(int dev, int op, int dtype, const SegBatch& b, const MapPa
   return KTB_ERR_UNSUPPORTED;
 }
 
-// Splits n segments into launches of <= kSegMax descriptors (and < 2^32 tiles).
-static int run_segments(int dev, int op, int dtype, const void* const* srcs, void* const* dsts,
-                        const size_t* nbytes, int n, const MapParams& p, cudaStream_t stream) {
+// Splits n segments into launches of <= CAP descriptors (and < 2^31 tiles).
+template <int CAP>
+static int run_segments_cap(int op, int dtype, const void* const* srcs, void* const* dsts,
+                            const size_t* nbytes, int n, const MapParams& p, cudaStream_t stream, SegBatch<CAP>& b) {
   const size_t es = (op == KTB_OP_IDENTITY) ? 1 : dtype_size(dtype);
-  SegBatch b;
   b.n = 0;
   b.tile_prefix[0] = 0;
   for (int i = 0; i < n; ++i) {
@@ -144,8 +152,8 @@ static int run_segments(int dev, int op, int dtype, const void* const* srcs, voi
                 KTB_ERR_ARG, "segment %d: not aligned to the element size %zu", i, es);
     const size_t tiles = (nbytes[i] + kSegTile - 1) / kSegTile;
     KTB_REQUIRE(tiles < 0x7fffffffULL, KTB_ERR_ARG, "segment %d: %zu bytes is too large", i, nbytes[i]);
-    if (b.n == kSegMax || (size_t)b.tile_prefix[b.n] + tiles >= 0x7fffffffULL) {
-      int rc = launch_seg(dev, op, dtype, b, p, stream);
+    if (b.n == CAP || (size_t)b.tile_prefix[b.n] + tiles >= 0x7fffffffULL) {
+      int rc = launch_seg<CAP>(op, dtype, b, p, stream);
       if (rc) return rc;
       b.n = 0;
     }
@@ -155,8 +163,21 @@ static int run_segments(int dev, int op, int dtype, const void* const* srcs, voi
     b.tile_prefix[b.n + 1] = b.tile_prefix[b.n] + (uint32_t)tiles;
     ++b.n;
   }
-  if (b.n > 0) return launch_seg(dev, op, dtype, b, p, stream);
+  if (b.n > 0) return launch_seg<CAP>(op, dtype, b, p, stream);
   return KTB_OK;
+}
+
+static int run_segments(int dev, int op, int dtype, const void* const* srcs, void* const* dsts,
+                        const size_t* nbytes, int n, const MapParams& p, cudaStream_t stream) {
+  (void)dev;
+  if (n > kSegSmall && g_seg_large) {
+    // 28 KiB descriptor block: per-thread scratch, reused across calls (the launch copies it)
+    static thread_local std::unique_ptr<SegBatch<kSegLarge>> big;
+    if (!big) big.reset(new SegBatch<kSegLarge>());
+    return run_segments_cap<kSegLarge>(op, dtype, srcs, dsts, nbytes, n, p, stream, *big);
+  }
+  SegBatch<kSegSmall> b;
+  return run_segments_cap<kSegSmall>(op, dtype, srcs, dsts, nbytes, n, p, stream, b);
 }
 
 }  // namespace ktb

@@ -14,9 +14,11 @@
 namespace ktb {
 
 constexpr int kRedThreads = 256;
-constexpr int kRedMaxGrid = 8192;
+constexpr int kRedMaxGrid = 4096;  // per-CTA partials: the last CTA folds them in ONE round of 8 x 16-byte loads per thread
 constexpr size_t kRedHeader = 64;  // counter lives in the first 64 bytes of the workspace
-int g_red_ctas_per_sm = 8;         // ktb_set_tuning key 6
+int g_red_ctas_per_sm = 4;         // ktb_set_tuning key 6: grid cap in units of 1024 CTAs (<= kRedMaxGrid)
+int g_red_fold = 1;                // ktb_set_tuning key 14: 0 = skip the cross-CTA fold (measurement only; result invalid)
+int g_red_loads = 8;               // ktb_set_tuning key 13: 256-bit loads in flight per thread (8 = 64 KiB tile per CTA, default; 4 = 32 KiB)
 
 template <int DT>
 struct Acc {
@@ -109,9 +111,9 @@ __device__ __forceinline__ T block_sum(T v, T* smem /* >= 32 entries */) {
   return r;
 }
 
-template <int DT, int OP>
+template <int DT, int OP, int LOADS>
 __global__ void __launch_bounds__(kRedThreads)
-    map_reduce_kernel(const uint8_t* src, size_t n_elems, MapParams mp, void* out, uint8_t* ws) {
+    map_reduce_kernel(const uint8_t* src, size_t n_elems, MapParams mp, void* out, uint8_t* ws, int fold) {
   using A = typename Acc<DT>::type;
   // cross-CTA partials are kept in fp64 for float sums, int64 for integer sums
   using P = typename std::conditional<std::is_same<A, float>::value, double, long long>::type;
@@ -125,21 +127,23 @@ __global__ void __launch_bounds__(kRedThreads)
 
   A acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
   const size_t stride = (size_t)gridDim.x * kRedThreads;
-  // CTA-contiguous tiles of 4 x 256 packets (32 KiB): 4 independent 256-bit loads in flight per thread, one tile per
-  // CTA when the grid covers the input (the hardware scheduler balances the tail), grid-stride beyond kRedMaxGrid
-  constexpr size_t kTilePackets = 4 * (size_t)kRedThreads;
+  // CTA-contiguous tiles of LOADS x 256 packets (32 or 64 KiB): LOADS independent 256-bit loads in flight per thread,
+  // one tile per CTA when the grid covers the input (the hardware scheduler balances the tail), grid-stride beyond
+  // kRedMaxGrid.  The four accumulators are filled round-robin so the summation order is fixed for a given LOADS.
+  constexpr size_t kTilePackets = (size_t)LOADS * kRedThreads;
   const size_t n_tiles = n_vec / kTilePackets;
   for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const size_t v = t * kTilePackets + threadIdx.x;
-    uint32_t w0[8], w1[8], w2[8], w3[8];
-    ldg256_stream(src + (v << 5), w0);
-    ldg256_stream(src + ((v + kRedThreads) << 5), w1);
-    ldg256_stream(src + ((v + 2 * kRedThreads) << 5), w2);
-    ldg256_stream(src + ((v + 3 * kRedThreads) << 5), w3);
-    acc0 += words_value<DT, OP, 8>(w0, mp);
-    acc1 += words_value<DT, OP, 8>(w1, mp);
-    acc2 += words_value<DT, OP, 8>(w2, mp);
-    acc3 += words_value<DT, OP, 8>(w3, mp);
+    uint32_t w[LOADS][8];
+#pragma unroll
+    for (int j = 0; j < LOADS; ++j) ldg256_stream(src + ((v + (size_t)j * kRedThreads) << 5), w[j]);
+#pragma unroll
+    for (int j = 0; j < LOADS; j += 4) {
+      acc0 += words_value<DT, OP, 8>(w[j], mp);
+      acc1 += words_value<DT, OP, 8>(w[j + 1], mp);
+      acc2 += words_value<DT, OP, 8>(w[j + 2], mp);
+      acc3 += words_value<DT, OP, 8>(w[j + 3], mp);
+    }
   }
   for (size_t v = n_tiles * kTilePackets + (size_t)blockIdx.x * kRedThreads + threadIdx.x; v < n_vec; v += stride) {
     uint32_t w0[8];
@@ -156,18 +160,40 @@ __global__ void __launch_bounds__(kRedThreads)
 
   unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
   P* partials = reinterpret_cast<P*>(ws + kRedHeader);
+  if (!fold) {  // measurement aid (ktb_set_tuning key 14): stream + per-CTA partial only
+    if (threadIdx.x == 0) partials[blockIdx.x] = part;
+    return;
+  }
   if (threadIdx.x == 0) {
     partials[blockIdx.x] = part;
-    __threadfence();
-    unsigned int ticket = atomicAdd(counter, 1u);
+    // one acq_rel RMW instead of fence + atomic + fence: releases this CTA's partial, and for the CTA that draws
+    // the last ticket acquires everyone else's (bar.sync below extends that to the other threads of the CTA)
+    unsigned int ticket;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(counter) : "memory");
     is_last = (ticket == gridDim.x - 1);
   }
   __syncthreads();
   if (is_last) {
-    __threadfence();
+    // fixed-order fold of the per-CTA partials: every thread issues ALL of its (<= 8) 16-byte L2 loads before the
+    // first add, so the tail of the launch is one memory round trip instead of one per 256 partials (16 x 16 B would
+    // cost 64 registers and halve the occupancy of the streaming phase; 8 keeps the kernel under 48)
+    using P2 = typename std::conditional<std::is_same<P, double>::value, double2, longlong2>::type;
+    constexpr int kFoldLoads = kRedMaxGrid / (2 * kRedThreads);
+    const unsigned int n = gridDim.x;
+    P2 v[kFoldLoads];
+#pragma unroll
+    for (int j = 0; j < kFoldLoads; ++j) {
+      const unsigned int i = 2 * threadIdx.x + (unsigned int)j * 2 * kRedThreads;
+      v[j].x = 0;
+      v[j].y = 0;
+      if (i + 1 < n)
+        v[j] = __ldcg(reinterpret_cast<const P2*>(&partials[i]));
+      else if (i < n)
+        v[j].x = __ldcg(&partials[i]);
+    }
     P s = 0;
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += kRedThreads)
-      s += *reinterpret_cast<volatile P*>(&partials[i]);
+#pragma unroll
+    for (int j = 0; j < kFoldLoads; ++j) s += v[j].x + v[j].y;
     s = block_sum<P>(s, red);
     if (threadIdx.x == 0) {
       if constexpr (std::is_same<A, float>::value)
@@ -191,13 +217,17 @@ __global__ void __launch_bounds__(kRedThreads) reduce_partials_kernel(const T* p
 template <int DT, int OP>
 static int launch_reduce_typed(int dev, const uint8_t* src, size_t n_elems, const MapParams& p,
                                void* out, void* ws, cudaStream_t stream) {
-  const DeviceInfo* di = device_info(dev);
-  (void)di;
+  (void)dev;
   constexpr size_t ES = (DT == KTB_BF16 || DT == KTB_F16) ? 2 : (DT == KTB_I64 ? 8 : 4);
-  const size_t tiles = (n_elems * ES + 32767) / 32768;   // one 32 KiB tile per CTA
+  const int loads = g_red_loads == 4 ? 4 : 8;
+  const size_t tile = (size_t)loads * kRedThreads * 32;  // one tile per CTA
+  const size_t tiles = (n_elems * ES + tile - 1) / tile;
   const size_t cap = g_red_ctas_per_sm > 0 ? std::min<size_t>((size_t)kRedMaxGrid, (size_t)g_red_ctas_per_sm * 1024) : kRedMaxGrid;
   int grid = (int)std::min<size_t>(std::max<size_t>(tiles, 1), cap);
-  map_reduce_kernel<DT, OP><<<grid, kRedThreads, 0, stream>>>(src, n_elems, p, out, (uint8_t*)ws);
+  if (loads == 8)
+    map_reduce_kernel<DT, OP, 8><<<grid, kRedThreads, 0, stream>>>(src, n_elems, p, out, (uint8_t*)ws, g_red_fold);
+  else
+    map_reduce_kernel<DT, OP, 4><<<grid, kRedThreads, 0, stream>>>(src, n_elems, p, out, (uint8_t*)ws, g_red_fold);
   KTB_CK(cudaGetLastError());
   return KTB_OK;
 }

@@ -204,6 +204,32 @@ def test_pack_unpack_roundtrip(K):
         assert torch.equal(v.cpu().view(torch.uint8), t.contiguous().view(torch.uint8))
 
 
+@pytest.mark.parametrize("count", [96, 97, 1024, 1025, 2500])
+@pytest.mark.parametrize("large", [1, 0])
+def test_pack_many_segments_descriptor_batches(K, count, large):
+    """> 96 segments ride in large kernel parameters (one launch per 1024); tuning 12 = 0 forces 96 per launch."""
+    g = torch.Generator().manual_seed(count)
+    sizes = torch.randint(1, 9000, (count,), generator=g).tolist()
+    sizes[count // 2] = 300_001          # one segment spanning many 32 KiB tiles
+    flat = torch.randint(0, 255, (sum(sizes) + 64,), generator=g, dtype=torch.uint8).cuda()
+    srcs, off = [], 0
+    for i, n in enumerate(sizes):
+        srcs.append(flat[off + (i % 3):off + (i % 3) + n])      # mixed 1/2/16/32-byte alignment
+        off += n
+    K.set_tuning(12, large)
+    try:
+        arena, offsets = K.pack(srcs)
+        outs = [torch.empty(n, dtype=torch.uint8, device="cuda") for n in sizes]
+        K.unpack(arena, offsets, outs)
+        torch.cuda.synchronize()
+    finally:
+        K.set_tuning(12, 1)
+    a = arena.cpu()
+    for t, o, dst in zip(srcs, offsets, outs):
+        assert torch.equal(a[o:o + t.numel()], t.cpu())
+        assert torch.equal(dst.cpu(), t.cpu())
+
+
 def test_map_batch(K):
     xs = [_rand(torch.float32, n, seed=n).cuda() for n in [1, 5, 256, 1000, 4096, 100_003] + [64] * 200]
     outs = K.map_batch(xs, "affine", 0.5, 2.0)
