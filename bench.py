@@ -416,6 +416,19 @@ def run_ours(args):
         small = {"payload_bytes": 1024, "one_launch_per_call_calls_per_sec": 1e3 / ms_single,
                  "coalesced_batch_calls_per_sec": 2048 * 1e3 / ms_batch, "device_timed": True}
         assert torch.equal(ys[5], xs[5] * 2)
+        # the same 1 KiB call through the public API (kt.fn -> .to -> remote(x)), host-clock timed, Python included
+        dbl = kt.mapped("scale", alpha=2.0)(_clone(cases.double))
+        r1 = kt.fn(dbl, name="bench-small").to(kt.Compute(gpus=1).distribute("b200", workers=1, num_proc=1))
+        for _ in range(200):
+            o = r1(xs[0], serialization="pickle")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5000):
+            o = r1(xs[0], serialization="pickle")
+        torch.cuda.synchronize()
+        small["public_api_calls_per_sec"] = 5000 / (time.perf_counter() - t0)
+        assert torch.equal(o[0], xs[0] * 2)
+        r1.teardown()
 
     # ---- CPU baseline (N=1 only), bounded sample ---------------------------------------------------------------------
     cpu = None

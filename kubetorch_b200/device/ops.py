@@ -39,6 +39,8 @@ def require_cuda():
 
 def ensure_init(devices: Sequence[int]) -> None:
     """Register devices with the library (enables NVLink peer access between all registered)."""
+    if _registered.issuperset(devices):  # per-call fast path: nothing to register
+        return
     require_cuda()
     devs = [int(d) for d in devices]
     with _init_lock:
@@ -56,9 +58,18 @@ def dtype_code(dtype: torch.dtype) -> int:
         raise TypeError(f"kubetorch_b200 mapped ops support {sorted(str(k) for k in _DTYPE_CODES)}, got {dtype}")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+def current_stream_handle(device: int) -> int:
+    """cudaStream_t of torch's current stream on `device` (the raw getter skips building a Stream object)."""
+    if _raw_stream is not None:
+        return int(_raw_stream(device))
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
 def _stream(device: int, stream: Optional[torch.cuda.Stream]) -> int:
-    s = stream if stream is not None else torch.cuda.current_stream(device)
-    return int(s.cuda_stream)
+    return int(stream.cuda_stream) if stream is not None else current_stream_handle(device)
 
 
 def _check_dev_tensor(t: torch.Tensor, name: str) -> int:
@@ -348,10 +359,10 @@ def scatter_map_gather(
     devs = [int(d) for d in devices]
     if devs[root_rank] != root:
         raise ValueError(f"x_root lives on cuda:{root} but devices[{root_rank}] is {devs[root_rank]}")
-    ensure_init(set(devs))
+    ensure_init(devs)
     if out_root is None:
         out_root = torch.empty_like(x_root)
-    streams = [int(torch.cuda.current_stream(d).cuda_stream) for d in devs]
+    streams = [current_stream_handle(d) for d in devs]
     L.call(
         "ktb_scatter_map_gather", OPS[op], dtype_code(x_root.dtype), x_root.data_ptr(), out_root.data_ptr(),
         x_root.numel(), int(granule or row_elems(x_root)), float(alpha), float(beta), len(devs), L.arr(ctypes.c_int, devs), root_rank, int(variant),

@@ -39,21 +39,28 @@ class MappedSpec:
         sig = self.extra.get("__sig__")
         if sig is None:  # inspect.signature costs ~15 us: once per callable, not per call
             sig = self.extra["__sig__"] = inspect.signature(fn)
-        bound = sig.bind(*args, **kwargs)
-        bound.apply_defaults()
-        names = list(sig.parameters)
+            self.extra["__names__"] = list(sig.parameters)
+            self.extra["__plain__"] = all(
+                p.kind is p.POSITIONAL_OR_KEYWORD and p.default is p.empty for p in sig.parameters.values())
+        names = self.extra["__names__"]
+        if not kwargs and len(args) == len(names) and self.extra["__plain__"]:
+            arguments = dict(zip(names, args))  # the common call shape: skip Signature.bind (~10 us)
+        else:
+            bound = sig.bind(*args, **kwargs)   # raises the same TypeError the callable itself would
+            bound.apply_defaults()
+            arguments = bound.arguments
         tensor_name = self.arg or names[0]
-        if tensor_name not in bound.arguments:
+        if tensor_name not in arguments:
             raise TypeError(f"mapped callable {fn.__name__}() is missing its tensor argument '{tensor_name}'")
 
         def resolve(v):
             if isinstance(v, str):
-                if v not in bound.arguments:
+                if v not in arguments:
                     raise TypeError(f"mapped callable {fn.__name__}(): parameter '{v}' not found in the call")
-                return bound.arguments[v]
+                return arguments[v]
             return v
 
-        return bound.arguments[tensor_name], resolve(self.alpha), resolve(self.beta), bound.arguments
+        return arguments[tensor_name], resolve(self.alpha), resolve(self.beta), arguments
 
 
 def mapped(op: str, alpha: Any = 1.0, beta: Any = 0.0, reduce: Optional[str] = None, arg: str = None, **extra):

@@ -134,6 +134,8 @@ class B200Supervisor:
 
         rows = x.shape[0] if x.dim() > 0 else 1
         y = flat_like.view(x.shape) if x.dim() > 0 else flat_like.view(1)
+        if self.world_size == 1:
+            return [y]
         views = []
         for r in range(self.world_size):
             b, e = ops.shard_bounds(rows, self.world_size, r)
@@ -151,8 +153,7 @@ class B200Supervisor:
         if x.dim() == 0:
             x = x.reshape(1)
         x = x.contiguous()
-        with torch.cuda.device(root):
-            out = torch.empty_like(x)
+        out = torch.empty_like(x)  # same device as x: the root GPU
         if self.placement == "root":
             ops.scatter_map_gather(x, op, alpha, beta, devices=[root] * len(self.devices), out_root=out,
                                    variant=self.variant)

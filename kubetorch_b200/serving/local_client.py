@@ -11,9 +11,8 @@ serialization allow-list with the reference's message.
 from __future__ import annotations
 
 import asyncio
-import hashlib
 import json
-import time
+import os
 from typing import Optional
 
 from .codec import MAGIC_CALL_KWARGS, SERIALIZATION_FORMATS, package_exception, rebuild_exception
@@ -36,7 +35,8 @@ class LocalClient:
         self.pod_name = pod_name or f"{service_name}-0"
 
     def _request_id(self, endpoint: str) -> str:
-        return hashlib.sha256(f"{endpoint}_{time.time()}".encode()).hexdigest()[:10]
+        # 10 hex digits, unique per call like the reference's sha256(endpoint, time)[:10] (http_client.py:311-349)
+        return os.urandom(5).hex()
 
     def call_method(self, endpoint: str, stream_logs=None, logging_config=None, stream_metrics=None, body: dict = None,
                     headers: dict = None, serialization: str = "json"):
