@@ -24,7 +24,7 @@ if which in ("all", "reduce"):
     for _ in range(4):
         ops.map_reduce_sum(x, "scale", 2.0)
 if which in ("all", "pack"):
-    ts = [torch.empty(1 << 18, dtype=torch.uint8, device="cuda") for _ in range(1024)]
+    ts = [torch.empty(1 << 18, dtype=torch.uint8, device="cuda") for _ in range(4096)]   # C4's shard list, 1 GiB
     plan = ops.PackPlan(ts)
     for _ in range(4):
         plan.run()
