@@ -33,6 +33,9 @@ constexpr int kMlpThreads = 192;
 int g_mlp_chunk_rows = 65536;  // ktb_set_tuning key 8: rows per chunk (2 x 128 MiB of hidden activations at d_hidden = 1024;
                                // measured best with the CTA-pair kernel: 940-964 TFLOP/s)
 int g_mlp_epi_groups = 1;      // ktb_set_tuning key 9: epilogue warpgroups (1 or 2); 2 measured 3% slower
+std::atomic<int> g_mlp_cluster4_max[kMaxDevices];   // co-resident clusters of 4 per device (occupancy query, cached)
+int g_mlp_stages = 4;          // ktb_set_tuning key 17: TMA ring depth of the CTA-pair kernel (4 or 5)
+int g_mlp_cluster4 = 0;        // ktb_set_tuning key 15: 1 = cluster-of-4 multicast form of the CTA-pair kernel (opt-in)
 int g_mlp_2sm = 1;             // ktb_set_tuning key 11: 1 = CTA-pair (cta_group::2) kernel for the 256-wide layers (default)
 int g_mlp_tma_store = 1;       // ktb_set_tuning key 10: 1 = TMA-store epilogue for the 256-wide layers (default)
 int g_mlp_persistent = 1;      // ktb_set_tuning key 7: 1 = persistent double-buffered kernel, 0 = one tile per CTA
@@ -761,6 +764,190 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * EPI_GROUP
   }
 }
 
+__device__ __forceinline__ void tma_load_2d_2sm_mc(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                                   uint32_t leader_bar_addr, uint16_t cta_mask) {
+  // same CTA-relative destination offset and barrier offset in every CTA of cta_mask; with cta_group::2 and the peer bit
+  // of the barrier address cleared, each destination signals the barrier of ITS pair's leader
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(leader_bar_addr), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_mask(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
+// Cluster-of-4 form of the CTA-pair kernel (opt-in, ktb_set_tuning key 15): two pairs share every B tile through TMA
+// multicast.  Everything else (TMEM double buffering, TMA-store epilogue) is the pair kernel's.
+template <int STAGES, bool RELU, int EPI_GROUPS>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(64 + 128 * EPI_GROUPS)
+    gemm_bf16_tn_2sm_mc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                            const __grid_constant__ CUtensorMap map_c, int K, int tiles_m, int tiles_n) {
+  constexpr int BLOCK_N = 256;                              // per pair; each CTA stages 128 of these B rows
+  constexpr int kABytes = kMlpBlockM * kMlpBlockK * 2;      // 16 KiB: this CTA's 128 rows of A
+  constexpr int kBBytes = 128 * kMlpBlockK * 2;             // 16 KiB: this CTA's half of B
+  constexpr int kStageBytes = kABytes + kBBytes;            // 32 KiB per CTA per stage
+  constexpr int kCBytes = kMlpBlockM * BLOCK_N * 2;         // 64 KiB C tile of this CTA (128 rows x 256 cols)
+  constexpr int kBoxBytes = kMlpBlockM * 64 * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ctile = smem + STAGES * kStageBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ctile + kCBytes);   // used on the leader only
+  uint64_t* empty = full + STAGES;                                  // per CTA
+  uint64_t* tmem_full = empty + STAGES;                             // [2], per CTA
+  uint64_t* tmem_empty = tmem_full + 2;                             // [2], used on the leader only
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // cluster of two CTA pairs: pair `p` = rank >> 1 takes rows [p*256, p*256+256) of a 512 x 256 cluster tile, `r` =
+  // rank & 1 is the CTA's place inside its pair.  Both pairs need the same 256 x 64 B tile per k-block: CTA (p, r)
+  // fetches ONE QUARTER of it (64 rows) and multicasts it into the B half of CTAs (0, r) and (1, r), so each B byte
+  // leaves the L2 once per cluster instead of once per pair (layer 2 is bound by the L2 -> SM fabric, not by the MMA).
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t p = rank >> 1, r = rank & 1;
+  const uint32_t leader_rank = rank & ~1u;
+  const bool leader = (r == 0);
+  const int num_kb = K / kMlpBlockK;
+  const int num_tiles = tiles_m * tiles_n;                 // 512 x 256 cluster tiles
+  const int pair = blockIdx.x >> 2;                        // (cluster index: both pairs walk the same tile sequence)
+  const int num_pairs = gridDim.x >> 2;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+    prefetch_tensormap(&map_c);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);          // the leader's producer arms it with the bytes of BOTH CTAs' loads
+      mbar_init(&empty[s], 2);         // one multicast commit from EACH pair: the stage is free cluster-wide
+    }
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 8 * EPI_GROUPS);      // 4 epilogue warps per group x 2 CTAs
+    mbar_init(&tmem_empty[1], 8 * EPI_GROUPS);
+    fence_barrier_init();
+  }
+  cluster_sync_all();                  // barriers of both CTAs are initialised before anyone signals across
+  if (warp == 1) tmem_alloc_2sm(tmem_holder, 2 * BLOCK_N);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile / tiles_n) * 512 + (int)p * 256 + (int)r * 128;
+        const int n0 = (tile % tiles_n) * BLOCK_N + (int)r * 128 + (int)p * 64;   // this CTA's quarter of B
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait_bounded(&empty[s], ((it / STAGES) & 1) ^ 1);
+          uint8_t* a_dst = smem + (size_t)s * kStageBytes;
+          // The pair leader expects every byte that lands in ITS pair for this k-block: two A tiles (one per CTA) and
+          // four B quarters (two per CTA, one of them multicast from the other pair) = 2 * kStageBytes.
+          if (leader) mbar_expect_tx(&full[s], 2 * kStageBytes);
+          const uint32_t leader_full_tma = smem_u32(&full[s]) & 0xFEFFFFFFu;   // peer bit cleared → CTA 0's barrier
+          tma_load_2d_2sm(a_dst, &map_a, kb * kMlpBlockK, m0, leader_full_tma);
+          tma_load_2d_2sm_mc(a_dst + kABytes + p * (kBBytes / 2), &map_b, kb * kMlpBlockK, n0, leader_full_tma,
+                             (uint16_t)((1u << r) | (1u << (2 + r))));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N);
+      int it = 0, t = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++t) {
+        const int as = t & 1;
+        mbar_wait_bounded(&tmem_empty[as], ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait_bounded(&full[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint8_t* a_src = smem + (size_t)s * kStageBytes;
+          const uint64_t adesc = make_smem_desc_sw128(a_src);
+          const uint64_t bdesc = make_smem_desc_sw128(a_src + kABytes);
+#pragma unroll
+          for (int k = 0; k < kMlpBlockK / kMlpUmmaK; ++k)
+            umma_f16_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          umma_commit_2sm_mask(&empty[s], (uint16_t)0xF);          // this pair is done with stage s, tell all 4 CTAs
+        }
+        umma_commit_2sm_mask(&tmem_full[as], (uint16_t)(3u << leader_rank));   // accumulator ready in both CTAs of the pair
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): own TMEM half → bf16 → swizzled shared C tile → TMA store =====
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int group = (warp - 2) >> 2;                     // each warpgroup converts its slice of the columns
+    constexpr int kColsPerGroup = BLOCK_N / EPI_GROUPS;
+    const bool issuer = (warp == 2 && lane == 0);
+    int t = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++t) {
+      const int as = t & 1;
+      const int m0 = (tile / tiles_n) * 512 + (int)p * 256 + (int)r * 128;
+      const int n0 = (tile % tiles_n) * BLOCK_N;
+      mbar_wait_bounded(&tmem_full[as], (t >> 1) & 1);
+      tc_fence_after();
+      if (issuer) bulk_wait_read<0>();
+      epi_barrier_n<128 * EPI_GROUPS>();
+#pragma unroll 1
+      for (int c = group * kColsPerGroup; c < (group + 1) * kColsPerGroup; c += 32) {
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c), acc);
+        uint8_t* box = ctile + (c >> 6) * kBoxBytes + row * 128;
+        const int chunk0 = (c & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float lo = __uint_as_float(acc[8 * q + 2 * j]);
+            float hi = __uint_as_float(acc[8 * q + 2 * j + 1]);
+            if (RELU) {
+              lo = fmaxf(lo, 0.f);
+              hi = fmaxf(hi, 0.f);
+            }
+            __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+            pk[j] = *reinterpret_cast<uint32_t*>(&v);
+          }
+          const int phys = (chunk0 + q) ^ (row & 7);
+          *reinterpret_cast<uint4*>(box + phys * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), leader_rank));   // pair leader's barrier
+      fence_proxy_async_smem();
+      epi_barrier_n<128 * EPI_GROUPS>();
+      if (issuer) {
+#pragma unroll
+        for (int b = 0; b < BLOCK_N / 64; ++b) tma_store_2d(&map_c, ctile + b * kBoxBytes, n0 + 64 * b, m0);
+        bulk_commit();
+      }
+    }
+    if (issuer) bulk_wait_all<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                  // both CTAs are done with TMEM and with each other's barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 2 * BLOCK_N);
+  }
+}
+
 // ---- host side --------------------------------------------------------------------------------------
 typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -857,8 +1044,45 @@ static int launch_gemm(int dev, const void* A, const void* B, void* C, size_t M,
     if (rc) return rc;
     rc = make_map(&mc, C, M, (uint64_t)N, kMlpBlockM);
     if (rc) return rc;
-    const int tiles_m = (int)(M / 256), tiles_n = N / 256;
     const int sms = device_info(dev) ? device_info(dev)->sm_count : 148;
+    if (g_mlp_cluster4 && M % 512 == 0) {
+      CUtensorMap mb4;
+      rc = make_map(&mb4, B, (uint64_t)N, (uint64_t)K, 64);    // each CTA loads a quarter of the B tile and multicasts it
+      if (rc) return rc;
+      auto kfn = gemm_bf16_tn_2sm_mc_kernel<ST, RELU, 1>;
+      static std::atomic<unsigned> attr_done{0};
+      rc = ensure_smem_attr(kfn, smem_bytes, attr_done, dev);
+      if (rc) return rc;
+      const int tiles_m4 = (int)(M / 512), tiles_n4 = N / 256;
+      std::atomic<int>* max_clusters = g_mlp_cluster4_max;
+      int mc4 = (dev >= 0 && dev < kMaxDevices) ? max_clusters[dev].load(std::memory_order_relaxed) : 0;
+      if (mc4 <= 0) {
+        // clusters of 4 cannot always cover all 148 SMs (GPC boundaries): ask the occupancy calculator once
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(sms & ~3));
+        cfg.blockDim = dim3(64 + 128);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 4;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int n_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, kfn, &cfg) != cudaSuccess || n_clusters <= 0) {
+          (void)cudaGetLastError();
+          n_clusters = sms / 4;
+        }
+        mc4 = n_clusters;
+        if (dev >= 0 && dev < kMaxDevices) max_clusters[dev].store(mc4, std::memory_order_relaxed);
+      }
+      const int grid4 = 4 * std::max(1, std::min(tiles_m4 * tiles_n4, mc4));
+      kfn<<<grid4, 64 + 128, smem_bytes, stream>>>(ma, mb4, mc, K, tiles_m4, tiles_n4);
+      KTB_CK(cudaGetLastError());
+      return KTB_OK;
+    }
+    const int tiles_m = (int)(M / 256), tiles_n = N / 256;
     const int grid = std::max(2, std::min(2 * tiles_m * tiles_n, sms & ~1));
     if (g_mlp_epi_groups == 2) {
       auto kfn = gemm_bf16_tn_2sm_kernel<ST, RELU, 2>;
@@ -869,13 +1093,23 @@ static int launch_gemm(int dev, const void* A, const void* B, void* C, size_t M,
     }
       kfn<<<grid, 64 + 256, smem_bytes, stream>>>(ma, mb2, mc, K, tiles_m, tiles_n);
     } else {
-      auto kfn = gemm_bf16_tn_2sm_kernel<ST, RELU, 1>;
-      {
-      static std::atomic<unsigned> attr_done{0};
-      rc = ensure_smem_attr(kfn, smem_bytes, attr_done, dev);
-      if (rc) return rc;
-    }
-      kfn<<<grid, 64 + 128, smem_bytes, stream>>>(ma, mb2, mc, K, tiles_m, tiles_n);
+      if (g_mlp_stages == 5) {
+        // five 32 KiB stages + the 64 KiB C tile = 225 KiB of the 227 KiB a CTA may own
+        constexpr int ST5 = 5;
+        constexpr int smem5 = ST5 * 32768 + kMlpBlockM * 256 * 2 + (2 * ST5 + 4) * 8 + 16 + 1024;
+        static_assert(smem5 <= 232448, "5-stage ring must fit the opt-in shared memory limit");
+        auto kfn = gemm_bf16_tn_2sm_kernel<ST5, RELU, 1>;
+        static std::atomic<unsigned> attr_done{0};
+        rc = ensure_smem_attr(kfn, smem5, attr_done, dev);
+        if (rc) return rc;
+        kfn<<<grid, 64 + 128, smem5, stream>>>(ma, mb2, mc, K, tiles_m, tiles_n);
+      } else {
+        auto kfn = gemm_bf16_tn_2sm_kernel<ST, RELU, 1>;
+        static std::atomic<unsigned> attr_done{0};
+        rc = ensure_smem_attr(kfn, smem_bytes, attr_done, dev);
+        if (rc) return rc;
+        kfn<<<grid, 64 + 128, smem_bytes, stream>>>(ma, mb2, mc, K, tiles_m, tiles_n);
+      }
     }
   } else if (g_mlp_persistent && g_mlp_tma_store && BLOCK_N == 256 && ldc == N) {
     constexpr int ST = 3;
