@@ -336,11 +336,19 @@ def test_mlp_tcgen05_matches_recorded_reference_and_fp32(K, golden):
         K.set_tuning(9, epi)
         assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got2)
     K.set_tuning(9, 1)
+    K.set_tuning(17, 5)  # five-stage TMA ring: same bits
+    assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got2)
+    K.set_tuning(17, 4)
+    K.set_tuning(15, 1)  # cluster of 4: two CTA pairs share each B tile through TMA multicast: same bits
+    assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got2)
+    K.set_tuning(15, 0)
     K.set_tuning(11, 0)
     K.set_tuning(10, 0)
     K.set_tuning(7, 0)  # one-tile-per-CTA kernel: same bits
     assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got2)
     K.set_tuning(7, 1)
+    K.set_tuning(10, 1)  # back to the shipped defaults for whatever runs next in this process
+    K.set_tuning(11, 1)
     # top-1 action agrees wherever the fp32 top-2 logit gap exceeds 2^-6
     top2 = want2.topk(2, dim=1).values
     clear = (top2[:, 0] - top2[:, 1]) > 2**-6
