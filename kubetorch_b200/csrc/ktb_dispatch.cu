@@ -119,7 +119,7 @@ struct CallEvents {
   cudaEvent_t make(int device) {
     DeviceGuard g(device);
     cudaEvent_t e = nullptr;
-    if (!g.ok || cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (n > kMaxDevices || !g.ok || cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     ev[n] = e;
     dev[n] = device;
     ++n;
@@ -281,11 +281,13 @@ int ktb_map_host(int dev, int op, int dtype, const void* src_host, void* dst_hos
   const MapParams p = make_params(alpha, beta, dtype);
   const size_t n_bytes = n_elems * es;
   const size_t n_chunks = (n_bytes + chunk_bytes - 1) / chunk_bytes;
+  CallEvents events;   // per-call events, destroyed on every exit path
   cudaEvent_t h2d_done[2], exec_done[2], d2h_done[2];
   for (int i = 0; i < 2; ++i) {
-    KTB_CK(cudaEventCreateWithFlags(&h2d_done[i], cudaEventDisableTiming));
-    KTB_CK(cudaEventCreateWithFlags(&exec_done[i], cudaEventDisableTiming));
-    KTB_CK(cudaEventCreateWithFlags(&d2h_done[i], cudaEventDisableTiming));
+    h2d_done[i] = events.make(dev);
+    exec_done[i] = events.make(dev);
+    d2h_done[i] = events.make(dev);
+    KTB_REQUIRE(h2d_done[i] && exec_done[i] && d2h_done[i], KTB_ERR_CUDA, "ktb_map_host: cudaEventCreate failed");
   }
   int status = KTB_OK;
   for (size_t c = 0; c < n_chunks && status == KTB_OK; ++c) {
@@ -320,11 +322,6 @@ int ktb_map_host(int dev, int op, int dtype, const void* src_host, void* dst_hos
   cudaError_t es1 = cudaStreamSynchronize(di->stream_d2h);
   cudaError_t es2 = cudaStreamSynchronize(di->stream_exec);
   cudaError_t es3 = cudaStreamSynchronize(di->stream_h2d);
-  for (int i = 0; i < 2; ++i) {
-    cudaEventDestroy(h2d_done[i]);
-    cudaEventDestroy(exec_done[i]);
-    cudaEventDestroy(d2h_done[i]);
-  }
   if (status == KTB_OK && (es1 != cudaSuccess || es2 != cudaSuccess || es3 != cudaSuccess)) {
     cudaError_t e = es1 != cudaSuccess ? es1 : (es2 != cudaSuccess ? es2 : es3);
     set_error("ktb_map_host: stream sync failed: %s", cudaGetErrorString(e));

@@ -3,7 +3,7 @@
 // ktb_scatter_map_gather (ktb_dispatch.cu) has every rank PULL its shard from the root (peer loads)
 // and PUSH its result back (peer stores): one kernel per rank, but the rank's NVLink port then carries
 // read requests + write data one way and read data + write acks the other, and measured only ~0.6 of
-// the link per direction (profiles/r1_peer_sweep.md).  Here both directions carry posted writes only:
+// the link per direction (profiles/r1f_sweep_peer_2gpu.jsonl).  Here both directions carry posted writes only:
 //
 //   root  : push_scatter_kernel  — for chunk c, peer-STORE chunk c of every rank's shard into that
 //           rank's staging buffer, then publish ready[r][c] = seq (st.release.sys) in the rank's memory

@@ -6,6 +6,7 @@
 #include "ktb_common.cuh"
 
 #include <stdarg.h>
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
 
@@ -22,6 +23,7 @@ void set_error(const char* fmt, ...) {
 
 static std::mutex g_mu;
 static DeviceInfo g_dev[kMaxDevices];
+static std::atomic<bool> g_registered[kMaxDevices];   // publication flag: set after g_dev[d] is fully built
 static bool g_peer[kMaxDevices][kMaxDevices];
 struct HostBlock { size_t nbytes; };
 static std::unordered_map<void*, size_t> g_arena[kMaxDevices];
@@ -30,7 +32,7 @@ static std::unordered_map<void*, int> g_ipc_open;
 
 DeviceInfo* device_info(int dev) {
   if (dev < 0 || dev >= kMaxDevices) return nullptr;
-  return g_dev[dev].registered ? &g_dev[dev] : nullptr;
+  return g_registered[dev].load(std::memory_order_acquire) ? &g_dev[dev] : nullptr;
 }
 
 int require_device(int dev) {
@@ -59,6 +61,7 @@ static int register_device(int dev) {
   for (int i = 0; i < 6; ++i) KTB_CK(cudaEventCreateWithFlags(&d.host_ev[i], cudaEventDisableTiming));
   d.registered = true;
   g_peer[dev][dev] = true;
+  g_registered[dev].store(true, std::memory_order_release);
   return KTB_OK;
 }
 
@@ -113,8 +116,16 @@ int ktb_init(int n_dev, const int* dev_ids) {
 
 int ktb_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& kv : g_ipc_open) {   // peers' arenas mapped into this process
+    if (kv.second >= 0 && kv.second < kMaxDevices && g_dev[kv.second].registered) {
+      DeviceGuard g(kv.second);
+      cudaIpcCloseMemHandle(kv.first);
+    }
+  }
+  g_ipc_open.clear();
   for (int d = 0; d < kMaxDevices; ++d) {
     if (!g_dev[d].registered) continue;
+    g_registered[d].store(false, std::memory_order_release);
     DeviceGuard g(d);
     cudaDeviceSynchronize();
     for (auto& kv : g_arena[d]) cudaFree(kv.first);
