@@ -24,6 +24,7 @@ extern int g_red_loads;        // ktb_reduce.cu
 extern int g_red_fold;         // ktb_reduce.cu
 extern int g_mlp_cluster4;     // ktb_mlp.cu
 extern int g_mlp_stages;       // ktb_mlp.cu
+extern int g_mlp_fuse_head;    // ktb_mlp.cu
 extern std::atomic<int> g_mlp_cluster4_max[kMaxDevices];
 extern int g_seg_large;        // ktb_pack.cu
 extern int g_mlp_persistent;   // ktb_mlp.cu
@@ -372,6 +373,7 @@ int ktb_set_tuning(int key, int value) {
     case 12: g_seg_large = value ? 1 : 0; return KTB_OK;
     case 13: g_red_loads = value == 4 ? 4 : 8; return KTB_OK;
     case 14: g_red_fold = value ? 1 : 0; return KTB_OK;
+    case 18: g_mlp_fuse_head = value ? 1 : 0; return KTB_OK;
     case 17: g_mlp_stages = value == 5 ? 5 : 4; return KTB_OK;
     case 15: g_mlp_cluster4 = value ? 1 : 0; return KTB_OK;
     case 16: return (value >= 0 && value < kMaxDevices) ? g_mlp_cluster4_max[value].load() : 0;   // query, after a cluster-4 launch

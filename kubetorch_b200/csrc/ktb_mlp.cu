@@ -30,10 +30,12 @@ constexpr int kMlpBlockM = 128;
 constexpr int kMlpBlockK = 64;   // 64 bf16 = 128 bytes = one SWIZZLE_128B row
 constexpr int kMlpUmmaK = 16;
 constexpr int kMlpThreads = 192;
-int g_mlp_chunk_rows = 65536;  // ktb_set_tuning key 8: rows per chunk (2 x 128 MiB of hidden activations at d_hidden = 1024;
-                               // measured best with the CTA-pair kernel: 940-964 TFLOP/s)
+int g_mlp_chunk_rows = 75776;  // ktb_set_tuning key 8: rows per chunk = 4 x 74 CTA pairs x 256 rows: the fused layer-2+head kernel
+                               // schedules whole 256-row blocks per pair, so a chunk is a whole number of waves on 148 SMs
+                               // (measured 1150 TFLOP/s; 65536 rows: 1059 fused, 940-964 unfused)
 int g_mlp_epi_groups = 1;      // ktb_set_tuning key 9: epilogue warpgroups (1 or 2); 2 measured 3% slower
 std::atomic<int> g_mlp_cluster4_max[kMaxDevices];   // co-resident clusters of 4 per device (occupancy query, cached)
+int g_mlp_fuse_head = 1;       // ktb_set_tuning key 18: 1 = layer 2 and the 64-wide head in one kernel (h2 stays on chip; default)
 int g_mlp_stages = 4;          // ktb_set_tuning key 17: TMA ring depth of the CTA-pair kernel (4 or 5)
 int g_mlp_cluster4 = 0;        // ktb_set_tuning key 15: 1 = cluster-of-4 multicast form of the CTA-pair kernel (opt-in)
 int g_mlp_2sm = 1;             // ktb_set_tuning key 11: 1 = CTA-pair (cta_group::2) kernel for the 256-wide layers (default)
@@ -948,6 +950,247 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(64 + 128 * EPI_GROUP
   }
 }
 
+// ---- layer 2 + head in ONE kernel (opt-in, ktb_set_tuning key 18) -----------------------------------------------------
+// h2 = relu(h1 @ W2^T) never goes to memory: the swizzled shared C tile the pair kernel stages for its TMA store is
+// already a valid K-major SWIZZLE_128B A operand, so after the epilogue has written it the MMA thread multiplies it
+// with the matching 256-column slice of W3 (logits[256 x 64] partial = C[256 x 256] @ W3[:, n0:n0+256]^T) into the
+// first 64 TMEM columns of the accumulator buffer that was just drained.  The partial products of the four N tiles of
+// a row block are summed in fp32 registers by the epilogue threads (one row each) and stored once as bf16.
+//   schedule (per pair, tiles walk N fastest):  main(t) | epi-1(t): drain + C tile | head MMA(t) issued in the MIDDLE of
+//   main(t+1) (the tensor pipe never waits for the epilogue) | epi-2(t): 64 columns -> registers, buffer released.
+// Barriers beyond the pair kernel's: c_ready (leader, 8 epilogue warps), l3_full (both CTAs, multicast commit),
+// w3_full (leader, TMA bytes of both CTAs' W3 rows).
+__device__ __forceinline__ void mbar_wait_bounded_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
+    mlp_l2_head_fused_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                             const __grid_constant__ CUtensorMap map_w3, __nv_bfloat16* __restrict__ out, int ldo,
+                             int K, int tiles_m, int tiles_n) {
+  constexpr int BLOCK_N = 256;
+  constexpr int kABytes = kMlpBlockM * kMlpBlockK * 2;      // 16 KiB: this CTA's 128 rows of A
+  constexpr int kBBytes = 128 * kMlpBlockK * 2;             // 16 KiB: this CTA's half of the W2 tile
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kCBytes = kMlpBlockM * BLOCK_N * 2;         // 64 KiB: relu(h2) tile of this CTA, 4 boxes of 128 x 64
+  constexpr int kBoxBytes = kMlpBlockM * 64 * 2;
+  constexpr int kW3Box = 32 * 64 * 2;                       // 4 KiB: this CTA's 32 W3 rows x 64 K columns
+  constexpr int kW3Bytes = 4 * kW3Box;                      // 16 KiB: 256 K columns
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ctile = smem + STAGES * kStageBytes;
+  uint8_t* w3s = ctile + kCBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(w3s + kW3Bytes);    // leader only
+  uint64_t* empty = full + STAGES;                                  // per CTA
+  uint64_t* tmem_full = empty + STAGES;                             // [2], per CTA
+  uint64_t* tmem_empty = tmem_full + 2;                             // [2], leader only
+  uint64_t* c_ready = tmem_empty + 2;                               // leader only
+  uint64_t* l3_full = c_ready + 1;                                  // per CTA
+  uint64_t* w3_full = l3_full + 1;                                  // leader only
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w3_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int num_kb = K / kMlpBlockK;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int n_units = pair < tiles_m ? (tiles_m - pair + num_pairs - 1) / num_pairs : 0;   // 256-row blocks of this pair
+  const int T = n_units * tiles_n;                                                          // tiles, N fastest
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+    prefetch_tensormap(&map_w3);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 8);      // 4 epilogue warps x 2 CTAs
+    mbar_init(&tmem_empty[1], 8);
+    mbar_init(c_ready, 8);
+    mbar_init(l3_full, 1);
+    mbar_init(w3_full, 1);
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 1) tmem_alloc_2sm(tmem_holder, 2 * BLOCK_N);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (lane == 0) {
+      const uint32_t leader_w3 = smem_u32(w3_full) & 0xFEFFFFFFu;
+      auto load_w3 = [&](int t) {      // this CTA's 32 rows of W3[:, tn*256 : tn*256+256]
+        const int tn = t % tiles_n;
+        if (leader) mbar_expect_tx(w3_full, 2 * kW3Bytes);
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          tma_load_2d_2sm(w3s + b * kW3Box, &map_w3, tn * BLOCK_N + 64 * b, (int)rank * 32, leader_w3);
+      };
+      int it = 0;
+      for (int t = 0; t < T; ++t) {
+        const int unit = pair + (t / tiles_n) * num_pairs;
+        const int m0 = unit * 256 + (int)rank * 128;
+        const int n0 = (t % tiles_n) * BLOCK_N + (int)rank * 128;
+        if (t == 0) load_w3(0);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait_bounded(&empty[s], ((it / STAGES) & 1) ^ 1);
+          uint8_t* a_dst = smem + (size_t)s * kStageBytes;
+          if (leader) mbar_expect_tx(&full[s], 2 * kStageBytes);
+          const uint32_t leader_full_tma = smem_u32(&full[s]) & 0xFEFFFFFFu;
+          tma_load_2d_2sm(a_dst, &map_a, kb * kMlpBlockK, m0, leader_full_tma);
+          tma_load_2d_2sm(a_dst + kABytes, &map_b, kb * kMlpBlockK, n0, leader_full_tma);
+        }
+        if (t >= 1) {
+          // the W3 buffer is free once the head MMA of tile t-1 has completed; that MMA is issued in the middle of
+          // main(t), whose loads are all in flight by now, so this wait cannot starve the pipeline
+          mbar_wait_bounded(l3_full, (uint32_t)((t - 1) & 1));
+          load_w3(t);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N);
+      constexpr uint32_t idesc3 = make_idesc_bf16(256, 64);
+      auto issue_head = [&](int j) {   // logits partial of tile j into the first 64 columns of its drained buffer
+        mbar_wait_bounded_cluster(c_ready, (uint32_t)(j & 1));
+        mbar_wait_bounded(w3_full, (uint32_t)(j & 1));
+        tc_fence_after();
+        const uint32_t d3 = tmem_base + (uint32_t)((j & 1) * BLOCK_N);
+#pragma unroll
+        for (int k = 0; k < BLOCK_N / kMlpUmmaK; ++k) {
+          const uint64_t adesc = make_smem_desc_sw128(ctile + (k >> 2) * kBoxBytes) + (uint64_t)(2 * (k & 3));
+          const uint64_t bdesc = make_smem_desc_sw128(w3s + (k >> 2) * kW3Box) + (uint64_t)(2 * (k & 3));
+          umma_f16_2sm(d3, adesc, bdesc, idesc3, (uint32_t)(k != 0));
+        }
+        umma_commit_2sm(l3_full);
+      };
+      int it = 0;
+      for (int t = 0; t < T; ++t) {
+        const int as = t & 1;
+        mbar_wait_bounded(&tmem_empty[as], ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          if (t >= 1 && kb == num_kb / 2) issue_head(t - 1);
+          const int s = it % STAGES;
+          mbar_wait_bounded(&full[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint8_t* a_src = smem + (size_t)s * kStageBytes;
+          const uint64_t adesc = make_smem_desc_sw128(a_src);
+          const uint64_t bdesc = make_smem_desc_sw128(a_src + kABytes);
+#pragma unroll
+          for (int k = 0; k < kMlpBlockK / kMlpUmmaK; ++k)
+            umma_f16_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          umma_commit_2sm(&empty[s]);
+        }
+        umma_commit_2sm(&tmem_full[as]);
+      }
+      if (T >= 1) issue_head(T - 1);
+    }
+  } else {
+    // ===== epilogue (both CTAs) =====
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    float acc3[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc3[i] = 0.f;
+    const uint32_t leader_c_ready = map_to_cta(smem_u32(c_ready), 0);
+    for (int t = 0; t < T; ++t) {
+      const int as = t & 1;
+      const int tn = t % tiles_n;
+      // ---- part 1: relu(accumulator) -> bf16 -> swizzled C tile (the head's A operand) ----
+      mbar_wait_bounded(&tmem_full[as], (t >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c), acc);
+        uint8_t* box = ctile + (c >> 6) * kBoxBytes + row * 128;
+        const int chunk0 = (c & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float lo = fmaxf(__uint_as_float(acc[8 * q + 2 * j]), 0.f);
+            const float hi = fmaxf(__uint_as_float(acc[8 * q + 2 * j + 1]), 0.f);
+            __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+            pk[j] = *reinterpret_cast<uint32_t*>(&v);
+          }
+          const int phys = (chunk0 + q) ^ (row & 7);
+          *reinterpret_cast<uint4*>(box + phys * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_c_ready);
+      // ---- part 2: head partial (64 columns) -> fp32 registers; the accumulator buffer is free afterwards ----
+      mbar_wait_bounded(l3_full, (uint32_t)(t & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t part[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + 32 * h), part);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc3[32 * h + i] += __uint_as_float(part[i]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));
+      if (tn == tiles_n - 1) {
+        const int unit = pair + (t / tiles_n) * num_pairs;
+        const size_t grow = (size_t)unit * 256 + (size_t)rank * 128 + (size_t)row;
+        uint4* dst = reinterpret_cast<uint4*>(out + grow * (size_t)ldo);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 v = __floats2bfloat162_rn(acc3[8 * q + 2 * j], acc3[8 * q + 2 * j + 1]);
+            pk[j] = *reinterpret_cast<uint32_t*>(&v);
+          }
+          dst[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+#pragma unroll
+        for (int i = 0; i < 64; ++i) acc3[i] = 0.f;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 2 * BLOCK_N);
+  }
+}
+
 // ---- host side --------------------------------------------------------------------------------------
 typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -1163,6 +1406,32 @@ static int launch_gemm(int dev, const void* A, const void* B, void* C, size_t M,
   return KTB_OK;
 }
 
+
+// Layer 2 + head fused (see mlp_l2_head_fused_kernel). h1 [M, d_hidden], W2 [d_hidden, d_hidden], W3 [64, d_hidden].
+static int launch_l2_head_fused(int dev, const void* h1, const void* W2, const void* W3, void* logits, size_t M,
+                                int d_hidden, int d_out, cudaStream_t stream) {
+  constexpr int ST = 4;
+  constexpr int smem_bytes = ST * 32768 + kMlpBlockM * 256 * 2 + 16384 + (2 * ST + 7) * 8 + 16 + 1024;
+  static_assert(smem_bytes <= 232448, "fused kernel must fit the opt-in shared memory limit");
+  CUtensorMap ma, mb, mw3;
+  int rc = make_map(&ma, h1, M, (uint64_t)d_hidden, kMlpBlockM);
+  if (rc) return rc;
+  rc = make_map(&mb, W2, (uint64_t)d_hidden, (uint64_t)d_hidden, 128);
+  if (rc) return rc;
+  rc = make_map(&mw3, W3, (uint64_t)d_out, (uint64_t)d_hidden, 32);
+  if (rc) return rc;
+  auto kfn = mlp_l2_head_fused_kernel<ST>;
+  static std::atomic<unsigned> attr_done{0};
+  rc = ensure_smem_attr(kfn, smem_bytes, attr_done, dev);
+  if (rc) return rc;
+  const int tiles_m = (int)(M / 256), tiles_n = d_hidden / 256;
+  const int sms = device_info(dev) ? device_info(dev)->sm_count : 148;
+  const int grid = 2 * std::max(1, std::min(tiles_m, sms / 2));
+  kfn<<<grid, 64 + 128, smem_bytes, stream>>>(ma, mb, mw3, static_cast<__nv_bfloat16*>(logits), d_out, d_hidden, tiles_m,
+                                              tiles_n);
+  KTB_CK(cudaGetLastError());
+  return KTB_OK;
+}
 }  // namespace ktb
 
 using namespace ktb;
@@ -1201,7 +1470,7 @@ static int mlp_run(int dev, const void* obs, size_t M, int d_in, int d_hidden, i
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaStream_t side = di->stream_exec;   // pulls the next chunk while this one computes
   // staged (NVLink pull) calls use smaller chunks: the first pull is exposed and more chunks overlap better
-  const size_t chunk = std::min<size_t>(M, stage ? std::min<size_t>((size_t)g_mlp_chunk_rows, 32768) : (size_t)g_mlp_chunk_rows);
+  const size_t chunk = std::min<size_t>(M, stage ? std::min<size_t>((size_t)g_mlp_chunk_rows, 37888) : (size_t)g_mlp_chunk_rows);
   __nv_bfloat16* h1 = static_cast<__nv_bfloat16*>(scratch);
   __nv_bfloat16* h2 = h1 + chunk * (size_t)d_hidden;
   const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(obs);
@@ -1244,6 +1513,11 @@ static int mlp_run(int dev, const void* obs, size_t M, int d_in, int d_hidden, i
     rc = launch_gemm<256, 4, true>(dev, a1, W1, h1, rows, d_hidden, d_in, d_hidden, st);
     if (rc) return rc;
     if (stg) KTB_CK(cudaEventRecord(evs[3 + (int)(c & 1)], st));
+    if (g_mlp_fuse_head && g_mlp_persistent && g_mlp_2sm && rows % 256 == 0 && d_out == 64) {
+      rc = launch_l2_head_fused(dev, h1, W2, W3, y + r0 * d_out, rows, d_hidden, d_out, st);
+      if (rc) return rc;
+      continue;
+    }
     rc = launch_gemm<256, 4, true>(dev, h1, W2, h2, rows, d_hidden, d_hidden, d_hidden, st);
     if (rc) return rc;
     rc = launch_gemm<64, 4, false>(dev, h2, W3, y + r0 * d_out, rows, d_out, d_hidden, d_out, st);
