@@ -169,3 +169,61 @@ def store_get_from_rank(src_rank, n):
 
 
 _KEEP = []
+
+
+# ---- pydantic payloads (kt tests/test_deployment_fixtures.py:116-205, tests/utils.py:83-86,254-290) -------------
+try:
+    from pydantic import BaseModel
+
+    class PairModel(BaseModel):
+        name: str
+        value: int
+
+    class OSInfoRequest(BaseModel):
+        method: str
+
+    class OSInfoResponse(BaseModel):
+        name: str
+        value: str
+except ImportError:  # pragma: no cover - pydantic is in the image
+    BaseModel = PairModel = OSInfoRequest = OSInfoResponse = None
+
+
+def model_summer(a, b):
+    """`summer` as the reference's test utilities write it: Pydantic models in → a model of the same type out."""
+    model_type = type(a) if hasattr(a, "model_dump") else None
+    a = a.value if hasattr(a, "model_dump") else a
+    b = b.value if hasattr(b, "model_dump") else b
+    if model_type is not None:
+        return model_type(name="sum_result", value=a + b)
+    return a + b
+
+
+class OSInfo:
+    """Stateful class with model-typed arguments and results (the reference's ResourceHungryGremlin.os_info shape)."""
+
+    def __init__(self, size=3):
+        self.size = size
+
+    def cpu_count(self):
+        import os
+
+        return os.cpu_count()
+
+    def size_minus_cpus(self):
+        import os
+
+        return self.size - os.cpu_count()
+
+    def os_info(self, requests):
+        import os
+
+        out = []
+        for req in requests:
+            if req.method == "uname":
+                out.append(OSInfoResponse(name="uname", value=str(os.uname())))
+            elif req.method == "cpu_count":
+                out.append(OSInfoResponse(name="cpu_count", value=str(os.cpu_count())))
+            elif req.method == "getpid":
+                out.append(OSInfoResponse(name="getpid", value=str(os.getpid())))
+        return out

@@ -181,6 +181,59 @@ def test_json_mode_normalises_like_http_and_rejects_unserialisable():
     f.teardown(); g.teardown()
 
 
+def test_serialization_formats_with_pydantic_models_like_the_reference_suite():
+    """kt tests/test_deployment_fixtures.py:116-205: ints and Pydantic models through pickle, class methods with model
+    lists, the module-level `.serialization` setting, per-call overrides, and serialization="none"."""
+    from pydantic import BaseModel
+
+    comp = kt.Compute(cpus=".01", allowed_serialization=["json", "pickle", "none"])
+    remote_fn = kt.fn(cases.model_summer, name="ser-fn").to(comp)
+    remote_cls = kt.cls(cases.OSInfo, name="ser-cls").to(
+        kt.Compute(cpus=".01", allowed_serialization=["json", "pickle", "none"]), init_args={"size": 3})
+    try:
+        assert remote_fn(2, 3, serialization="pickle") == 5
+        out = remote_fn(cases.PairModel(name="test_a", value=42), cases.PairModel(name="test_b", value=42),
+                        serialization="pickle")
+        assert isinstance(out, cases.PairModel) and out.name == "sum_result" and out.value == 84
+        cpu_count = remote_cls.cpu_count(serialization="pickle")
+        assert isinstance(cpu_count, int)
+        reqs = [cases.OSInfoRequest(method=m) for m in ("uname", "cpu_count", "getpid")]
+        res = remote_cls.os_info(reqs, serialization="pickle")
+        assert isinstance(res, list) and all(isinstance(r, BaseModel) for r in res)
+        assert [r.name for r in res] == ["uname", "cpu_count", "getpid"] and res[1].value == str(cpu_count)
+        with pytest.raises(TypeError):  # models are not JSON-serialisable: the json route refuses them like httpx would
+            remote_fn(cases.PairModel(name="a", value=1), cases.PairModel(name="b", value=2), serialization="json")
+        # module-level default, still overridable per call
+        original = remote_fn.serialization
+        remote_fn.serialization = "pickle"
+        try:
+            out = remote_fn(cases.PairModel(name="test_a", value=42), cases.PairModel(name="test_b", value=42))
+            assert isinstance(out, cases.PairModel) and out.value == 84
+            assert remote_fn(3, 4, serialization="json") == 7
+            assert remote_fn(3, 4, serialization="none") == 7
+        finally:
+            remote_fn.serialization = original
+        # the same models across real rank processes (pickled through the worker pipes), one result per rank
+        spmd = kt.fn(cases.model_summer, name="ser-fn-spmd").to(
+            kt.Compute(cpus="1", allowed_serialization=["json", "pickle"]).distribute("spmd", workers=1, num_proc=2))
+        try:
+            outs = spmd(cases.PairModel(name="x", value=40), cases.PairModel(name="y", value=2), serialization="pickle")
+            assert [type(o) for o in outs] == [cases.PairModel] * 2 and [o.value for o in outs] == [42, 42]
+        finally:
+            spmd.teardown()
+        remote_cls.serialization = "pickle"
+        try:
+            res = remote_cls.os_info([cases.OSInfoRequest(method="cpu_count")])
+            assert isinstance(res[0], BaseModel) and res[0].value == str(cpu_count)
+            assert isinstance(remote_cls.size_minus_cpus(serialization="json"), int)
+            assert isinstance(remote_cls.size_minus_cpus(serialization="none"), int)
+        finally:
+            remote_cls.serialization = "json"
+    finally:
+        remote_fn.teardown()
+        remote_cls.teardown()
+
+
 def test_async_callables_overlap_and_sync_calls_run_concurrently():
     f = kt.fn(cases.async_summer, name="as").to(kt.Compute(cpus=1).distribute("spmd", num_proc=1))
     try:
