@@ -77,10 +77,8 @@ __global__ void __launch_bounds__(kPushThreads)
   while (seg + 1 < a.n && a.tile_prefix[seg + 1] <= t) ++seg;
   // do not overwrite staging buffer (seq & 1) before the rank consumed call seq-2
   if (a.seq > 2) {
-    __shared__ bool ok;
-    if (threadIdx.x == 0) ok = spin_until(a.ack[seg], a.seq - 2, status);
+    if (threadIdx.x == 0) (void)spin_until(a.ack[seg], a.seq - 2, status);   // a timeout is recorded in *status
     __syncthreads();
-    (void)ok;
   }
   const size_t off = (size_t)(t - a.tile_prefix[seg]) * kPushTile;
   const size_t seg_bytes = (size_t)a.nbytes[seg];
