@@ -45,13 +45,35 @@ class DebugConfig:
 
 
 class KubetorchConfig:
-    """Minimal stand-in for kt.config (kt/config.py:13-383): explicit setter > KT_* env > default."""
+    """Minimal stand-in for kt.config (kt/config.py:13-383) with the reference's precedence:
+    explicit setter > KT_* env > ~/.kt/config.yaml > default."""
 
+    CONFIG_FILE = "~/.kt/config.yaml"
     _DEFAULTS = {"stream_logs": True, "stream_metrics": False, "namespace": "default", "username": None,
                  "backend": "auto"}
 
     def __init__(self):
         self._explicit = {}
+        self._file_cache = None
+
+    def _from_file(self) -> dict:
+        if self._file_cache is None:
+            path = os.path.expanduser(self.CONFIG_FILE)
+            data = {}
+            if os.path.exists(path):
+                try:
+                    import yaml
+
+                    with open(path) as f:
+                        data = yaml.safe_load(f) or {}
+                except Exception:  # noqa: BLE001 - an unreadable config file is ignored, as in the reference
+                    data = {}
+            self._file_cache = data if isinstance(data, dict) else {}
+        return self._file_cache
+
+    def refresh(self):
+        """Forget the cached file contents (tests; the reference caches per process too)."""
+        self._file_cache = None
 
     def __getattr__(self, name):
         if name.startswith("_"):
@@ -61,6 +83,8 @@ class KubetorchConfig:
         env = os.getenv(f"KT_{name.upper()}")
         if env is not None:
             return {"true": True, "false": False}.get(env.lower(), env)
+        if name in self._from_file():
+            return self._file_cache[name]
         if name in self._DEFAULTS:
             return self._DEFAULTS[name]
         raise AttributeError(f"kt.config has no setting '{name}'")

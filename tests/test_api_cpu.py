@@ -280,6 +280,25 @@ def test_compute_and_distribute_config_surface():
         assert name in kt.EXCEPTION_REGISTRY and kt.EXCEPTION_REGISTRY[name].__module__ == "kubetorch_b200"
 
 
+def test_config_precedence_setter_env_file_default(tmp_path, monkeypatch):
+    """kt/config.py:13-25,76-95: explicit setter > KT_* env > ~/.kt/config.yaml > default."""
+    from kubetorch_b200.config import KubetorchConfig
+
+    cfg_file = tmp_path / "config.yaml"
+    cfg_file.write_text("namespace: from-file\nstream_logs: false\n")
+    monkeypatch.setattr(KubetorchConfig, "CONFIG_FILE", str(cfg_file))
+    monkeypatch.delenv("KT_NAMESPACE", raising=False)
+    monkeypatch.delenv("KT_STREAM_LOGS", raising=False)
+    cfg = KubetorchConfig()
+    assert cfg.namespace == "from-file" and cfg.stream_logs is False and cfg.stream_metrics is False
+    monkeypatch.setenv("KT_NAMESPACE", "from-env")
+    assert cfg.namespace == "from-env"
+    cfg.namespace = "explicit"
+    assert cfg.namespace == "explicit"
+    with pytest.raises(AttributeError):
+        cfg.no_such_setting
+
+
 def test_tensor_wire_split_and_join_roundtrip():
     import pickle
 
