@@ -118,6 +118,93 @@ GROUPS = {
 }
 
 
+# Two real pods (uvicorn on 127.0.0.1 / 127.0.0.2, the recipe of SURVEY.md §8(c)) x 2 ranks each: pins the cross-pod
+# half of the path (kt/serving/remote_worker_pool.py:116-510, spmd_supervisor.py:219-261 `workers=` selectors,
+# rank ordering across pods).  group -> (callable, distributed config, n_pods, cases)
+MULTIPOD_GROUPS = {
+    "mp_env_2x2": ("env_report", {"distribution_type": "pytorch", "num_proc": 2, "quorum_workers": 2}, 2, [
+        ("mp_env_all", None, [], {}, "json"),
+        ("mp_env_workers_0", None, [], {"workers": [0]}, "json"),
+        ("mp_env_workers_str1", None, [], {"workers": ["1"]}, "json"),
+        ("mp_env_workers_0_1", None, [], {"workers": [0, 1]}, "json"),
+        ("mp_env_workers_any", None, [], {"workers": "any"}, "json"),
+        ("mp_env_workers_bad", None, [], {"workers": [10]}, "json"),
+    ]),
+    "mp_double_2x2": ("double", {"distribution_type": "spmd", "num_proc": 2, "quorum_workers": 2}, 2, [
+        ("mp_double_f32_1003_2x2", None, ["@f32_1003"], {}, "pickle"),
+        ("mp_double_f32_1003_workers_1", None, ["@f32_1003"], {"workers": [1]}, "pickle"),
+    ]),
+}
+
+
+def run_multipod_group(group: str, out_path: str):
+    """Child process: start one uvicorn pod per IP, POST to pod 0 as the client would, record, stop the pods."""
+    import socket
+    import time
+
+    import httpx
+    from kubetorch.resources.callables.utils import build_call_body
+    from kubetorch.serving.utils import _deserialize_response, _serialize_body
+
+    name, dist_cfg, n_pods, cases = MULTIPOD_GROUPS[group]
+    ips = [f"127.0.0.{k + 1}" for k in range(n_pods)]
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    base = dict(os.environ)
+    base.update({
+        "KT_LOG_STREAMING_ENABLED": "false", "KT_METRICS_ENABLED": "false", "POD_NAMESPACE": "kubetorch",
+        "LOCAL_IPS": ",".join(ips), "KT_SERVICE_NAME": "golden", "KT_FILE_PATH": REPO, "KT_MODULE_NAME": "oracle.cases",
+        "KT_CLS_OR_FN_NAME": name, "KT_INIT_ARGS": "null", "KT_ALLOWED_SERIALIZATION": "json,pickle",
+        "KT_DISTRIBUTED_CONFIG": json.dumps(dist_cfg), "KT_SERVER_PORT": str(port),
+    })
+    pods = []
+    try:
+        for k, ip in enumerate(ips):
+            env = dict(base)
+            env.update({"POD_IP": ip, "POD_NAME": f"golden-pod-{k}"})
+            pods.append(subprocess.Popen(
+                [sys.executable, "-m", "uvicorn", "kubetorch.serving.http_server:app", "--host", ip, "--port", str(port),
+                 "--log-level", "warning"], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+        deadline = time.time() + 180
+        for ip in ips:                      # every pod answers its health route before the first call
+            while True:
+                try:
+                    if httpx.get(f"http://{ip}:{port}/health", timeout=2).status_code == 200:
+                        break
+                except Exception:  # noqa: BLE001
+                    pass
+                if time.time() > deadline:
+                    raise RuntimeError(f"pod {ip} did not come up")
+                time.sleep(0.5)
+        inputs = _inputs()
+        results = {}
+        for case, method, arg_spec, kwargs, ser in cases:
+            args = _resolve(arg_spec, inputs)
+            body = _serialize_body(build_call_body(*args, **dict(kwargs)), ser)
+            url = f"http://{ips[0]}:{port}/{name}" + (f"/{method}" if method else "")
+            resp = httpx.post(url, json=body, headers={"X-Serialization": ser, "X-Request-ID": case}, timeout=300)
+            rec = {"callable": name, "method": method, "distributed_config": dist_cfg, "allowed": "json,pickle",
+                   "args": arg_spec, "kwargs": kwargs, "serialization": ser, "status_code": resp.status_code,
+                   "pods": ips}
+            if resp.status_code == 200:
+                rec["result"] = _deserialize_response(resp, ser)
+            else:
+                err = resp.json()
+                rec["error"] = {k: err.get(k) for k in ("error_type", "message", "pod_name", "detail") if k in err}
+            results[case] = rec
+        with open(out_path, "wb") as f:
+            pickle.dump(results, f)
+    finally:
+        for p in pods:
+            p.terminate()
+        for p in pods:
+            try:
+                p.wait(timeout=20)
+            except subprocess.TimeoutExpired:
+                p.kill()
+
+
 def _resolve(spec, inputs):
     """Replace "@name" strings (at any depth of lists/dicts) by the named input tensor."""
     if isinstance(spec, str) and spec.startswith("@"):
@@ -173,7 +260,7 @@ def main():
     import torch
 
     if len(sys.argv) == 4 and sys.argv[1] == "--group":
-        run_group(sys.argv[2], sys.argv[3])
+        (run_multipod_group if sys.argv[2] in MULTIPOD_GROUPS else run_group)(sys.argv[2], sys.argv[3])
         return
     if not os.path.isdir(REFERENCE):
         raise SystemExit(f"{REFERENCE} not found: goldens can only be regenerated where the reference is mounted")
@@ -185,10 +272,11 @@ def main():
     env["HOME"] = work
     env["PYTHONDONTWRITEBYTECODE"] = "1"
     all_results = {}
-    only = [a for a in sys.argv[1:] if a in GROUPS or a == "--helpers-only"]
+    ALL = {**GROUPS, **MULTIPOD_GROUPS}
+    only = [a for a in sys.argv[1:] if a in ALL or a == "--helpers-only"]
     if only and os.path.exists(OUT):
         all_results.update(torch.load(OUT, weights_only=False)["cases"])   # keep the other groups' records
-    for group in ([g for g in only if g in GROUPS] if only else GROUPS):
+    for group in ([g for g in only if g in ALL] if only else ALL):
         out_path = os.path.join(work, f"{group}.pkl")
         print(f"[make_golden] {group} ...", flush=True)
         subprocess.run([sys.executable, os.path.abspath(__file__), "--group", group, out_path], env=env, check=True,

@@ -363,6 +363,50 @@ def spmd_call(
     return deserialize_response(_wire(responses), serialization)
 
 
+def multipod_call(
+    fn,
+    *args,
+    num_proc: int = 1,
+    pod_ips: List[str],
+    distribution_type: str = "spmd",
+    serialization: str = "pickle",
+    port: Optional[int] = None,
+    allowed: Optional[str] = None,
+    **kwargs,
+) -> List[Any]:
+    """K pods x num_proc ranks in the flat topology (fewer pods than tree_minimum), called on pod_ips[0].
+
+    kt/serving/spmd/spmd_supervisor.py:126-170 (coordinator: sort the discovered IPs, move itself to the front, publish
+    them as POD_IPS), :219-261 (`workers=` narrows the remote pods and may exclude the coordinator's own ranks),
+    :270-276 (node_rank = position in that list), :341-365 (same params to every local rank), remote pods run the same
+    supervisor as a distributed_subcall with the coordinator's POD_IPS (remote_worker_pool.py:254-316), and
+    :557 `responses = local_responses + worker_responses`: the coordinator's ranks first, then the pods in list order."""
+    this_pod_ip = pod_ips[0]
+    worker_ips = sorted(pod_ips)
+    worker_ips.remove(this_pod_ip)
+    worker_ips.insert(0, this_pod_ip)
+    body = _wire(serialize_body(build_call_body(*args, **kwargs), serialization))
+    try:
+        subcall_ips, call_local = select_workers(body.get("workers"), worker_ips, this_pod_ip)
+    except ValueError as e:
+        status, envelope = package_exception(e)
+        raise _with_status(rehydrate_exception(envelope), status)
+    responses = []
+    for ip in ([this_pod_ip] if call_local else []) + list(subcall_ips):
+        node_rank = worker_ips.index(ip)
+        pod_params = body if ip == this_pod_ip else _wire(body)     # one more JSON hop to a remote pod
+        pod_responses = []
+        for local_rank in range(num_proc):
+            params = pickle.loads(pickle.dumps(pod_params))           # mp.Queue pickles the params once per rank
+            env = rank_env(distribution_type, worker_ips, node_rank, local_rank, num_proc, port)
+            res = _execute_rank(fn, params, serialization, env, allowed)
+            if isinstance(res, tuple) and res and res[0] == "__error__":
+                raise _with_status(rehydrate_exception(res[2]), res[1])
+            pod_responses.append(res)
+        responses.extend(pod_responses if ip == this_pod_ip else _wire(pod_responses))
+    return deserialize_response(_wire(responses), serialization)
+
+
 # ---- the same path with real processes (timed CPU baseline) -----------------------------------------
 def _oracle_worker(idx: int, req_q, resp_q, module_name: str, fn_name: str, extra_path: str):
     if extra_path and extra_path not in sys.path:

@@ -21,7 +21,8 @@ def _base_name(exc):
 def _compute_for(cfg, allowed=None):
     comp = kt.Compute(cpus="1", allowed_serialization=(allowed.split(",") if allowed else None))
     if cfg["distribution_type"] != "local":
-        comp.distribute(cfg["distribution_type"], workers=1, num_proc=cfg["num_proc"])
+        # records taken on K real pods carry quorum_workers=K: the local backend emulates K nodes on 127.0.0.k
+        comp.distribute(cfg["distribution_type"], workers=cfg.get("quorum_workers", 1), num_proc=cfg["num_proc"])
     return comp
 
 

@@ -36,10 +36,12 @@ def test_recorded_reference_calls_through_public_api(golden):
     }
     n = 0
     for name, rec in golden["cases"].items():
-        if rec["status_code"] != 200 or rec["callable"] not in specs:
-            continue
+        if rec["status_code"] != 200 or rec["callable"] not in specs or (rec.get("kwargs") or {}).get("workers"):
+            continue  # `workers=` sub-selections are host logic, covered on the CPU backends
         args = resolve_args(golden, rec["args"])
-        remote = _deploy(specs[rec["callable"]], rec["distributed_config"]["num_proc"], f"t-{name}")
+        # records taken on K real pods x P ranks have world size K*P: same shards, here as K*P local ranks
+        world = rec["distributed_config"]["num_proc"] * len(rec.get("pods") or [None])
+        remote = _deploy(specs[rec["callable"]], world, f"t-{name}")
         try:
             for resident in ("device", "host"):
                 call_args = [a.cuda() if (resident == "device" and isinstance(a, torch.Tensor)) else a for a in args]

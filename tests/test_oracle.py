@@ -31,6 +31,10 @@ def _run_oracle(rec, args):
         target = fn
     if cfg["distribution_type"] == "local":
         return R.local_call(target, *args, serialization=ser, allowed=rec.get("allowed"), **kwargs)
+    if rec.get("pods"):   # recorded on several real pods (uvicorn on 127.0.0.k)
+        return R.multipod_call(target, *args, num_proc=cfg["num_proc"], pod_ips=rec["pods"],
+                               distribution_type=cfg["distribution_type"], serialization=ser,
+                               allowed=rec.get("allowed"), **kwargs)
     return R.spmd_call(target, *args, num_proc=cfg["num_proc"], distribution_type=cfg["distribution_type"],
                        serialization=ser, allowed=rec.get("allowed"), **kwargs)
 
