@@ -112,6 +112,21 @@ GROUPS = {
         ("async_summer_1", None, [1, 2], {"sleep_time": 0.01}, "json"),
         ("async_summer_2", None, [10, 20], {"sleep_time": 0.01}, "json"),
     ]),
+    # real torch.distributed (gloo) rank processes brought up from the env contract by the reference launcher
+    "torch_ddp_pt4": ("torch_ddp", {"distribution_type": "pytorch", "num_proc": 4}, "json,pickle", [
+        ("torch_ddp_valid_recorded", None, [3], {}, "json"),
+        ("torch_ddp_invalid_recorded", None, ["a"], {}, "json"),
+    ]),
+    "all_reduce_pt4": ("all_reduce_rank", {"distribution_type": "pytorch", "num_proc": 4}, "json,pickle", [
+        ("all_reduce_rank_pt4", None, [], {}, "json"),
+    ]),
+    # per-rank state of a class persists across calls (ordered sequence on one deployment)
+    "number_state_spmd2": ("Number", {"distribution_type": "spmd", "num_proc": 2}, "json,pickle", [
+        ("number_state_0_count", "count", [], {}, "json"),
+        ("number_state_1_add", "add", [2, 3], {}, "json"),
+        ("number_state_2_add", "add", [4, 5], {}, "json"),
+        ("number_state_3_count", "count", [], {}, "json"),
+    ]),
     "mlp_spmd2": ("mlp_policy", {"distribution_type": "spmd", "num_proc": 2}, "json,pickle", [
         ("mlp_bf16_256_x2", None, ["@mlp_obs", "@mlp_w1", "@mlp_w2", "@mlp_w3"], {}, "pickle"),
     ]),

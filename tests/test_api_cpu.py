@@ -83,8 +83,8 @@ def test_recorded_reference_runtime_through_api(golden, deployed):
             "env_pytorch_4", "workers_any", "env_spmd_2"}  # POD_IPS/MASTER_ADDR are 127.0.0.x here, checked below
     n = 0
     for name, rec in golden["cases"].items():
-        if name in skip or name.startswith("mlp_"):
-            continue
+        if name in skip or name.startswith(("mlp_", "number_state_", "torch_ddp_", "all_reduce_")):
+            continue  # the last three groups are replayed by test_recorded_process_groups_and_class_state
         mod = deployed(rec["callable"], rec["distributed_config"], rec["allowed"])
         args = resolve_args(golden, rec["args"])
         if rec["status_code"] == 200:
@@ -97,6 +97,41 @@ def test_recorded_reference_runtime_through_api(golden, deployed):
             assert ei.value.status_code == rec["status_code"], name
         n += 1
     assert n >= 25
+
+
+def test_recorded_process_groups_and_class_state(golden):
+    """Records that need their own deployment: real torch.distributed (gloo) ranks brought up from the env contract
+    (each deployment owns MASTER_PORT 12345 while it lives), and an ORDERED call sequence on a stateful class."""
+    def fresh(rec, name):
+        obj = getattr(cases, rec["callable"])
+        mod = kt.cls(obj, name=name) if isinstance(obj, type) else kt.fn(obj, name=name)
+        return mod.to(_compute_for(rec["distributed_config"], rec["allowed"]))
+
+    for group in (("torch_ddp_valid_recorded", "torch_ddp_invalid_recorded"), ("all_reduce_rank_pt4",)):
+        mod = fresh(golden["cases"][group[0]], f"pg-{group[0]}")
+        try:
+            for name in group:
+                rec = golden["cases"][name]
+                args = resolve_args(golden, rec["args"])
+                if rec["status_code"] == 200:
+                    assert _call(mod, rec, args) == rec["result"], name
+                else:
+                    with pytest.raises(Exception) as ei:
+                        _call(mod, rec, args)
+                    assert _base_name(ei.value) == rec["error"]["error_type"], name
+                    assert ei.value.args[0].split("\n\n")[0] == rec["error"]["message"], name
+                    assert ei.value.status_code == rec["status_code"], name
+        finally:
+            mod.teardown()
+    seq = sorted(n for n in golden["cases"] if n.startswith("number_state_"))
+    assert len(seq) == 4
+    mod = fresh(golden["cases"][seq[0]], "number-state")
+    try:
+        for name in seq:   # count → add → add → count on the same per-rank instances
+            rec = golden["cases"][name]
+            assert _call(mod, rec, resolve_args(golden, rec["args"])) == rec["result"], name
+    finally:
+        mod.teardown()
 
 
 def test_env_contract_matches_reference_modulo_addresses(golden, deployed):
