@@ -105,7 +105,11 @@ def test_recorded_process_groups_and_class_state(golden):
     def fresh(rec, name):
         obj = getattr(cases, rec["callable"])
         mod = kt.cls(obj, name=name) if isinstance(obj, type) else kt.fn(obj, name=name)
-        return mod.to(_compute_for(rec["distributed_config"], rec["allowed"]))
+        cfg = rec["distributed_config"]
+        comp = kt.Compute(cpus="1", allowed_serialization=rec["allowed"].split(","))
+        # own rendezvous port: other deployments of this module may still hold the default 12345
+        extra = {"port": 29541} if cfg["distribution_type"] == "pytorch" else {}
+        return mod.to(comp.distribute(cfg["distribution_type"], workers=1, num_proc=cfg["num_proc"], **extra))
 
     for group in (("torch_ddp_valid_recorded", "torch_ddp_invalid_recorded"), ("all_reduce_rank_pt4",)):
         mod = fresh(golden["cases"][group[0]], f"pg-{group[0]}")
