@@ -21,6 +21,7 @@ from concurrent.futures import FIRST_EXCEPTION, wait
 from typing import Dict, List, Optional
 
 from .codec import HTTPException, check_allowed
+from . import fastpickle
 from .process_pool import ProcessPool
 from .supervisors import SPMDSupervisor, check_callable_name, select_worker_nodes
 from .tensor_wire import collect_refs, join_tensors, split_tensors
@@ -154,7 +155,7 @@ class GpuSPMDSupervisor(SPMDSupervisor):
             for r in ranks:
                 if r in self._pending_updates:
                     extras.setdefault(r, {})["arena_update"] = self._pending_updates.pop(r)
-            payload = pickle.dumps(skeleton, protocol=5)
+            payload = fastpickle.dumps(skeleton)   # CPU tensor leaves as raw bytes; CUDA leaves were moved to the arena
             envs = self.rank_envs()
             futures = self.pool.call_all(payload, method_name, envs, serialization, ranks=ranks, extras=extras)
             done, _ = wait(futures, return_when=FIRST_EXCEPTION)

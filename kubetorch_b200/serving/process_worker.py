@@ -25,6 +25,7 @@ from typing import Any, Dict, Optional
 
 from ..exceptions import SerializationError
 from .codec import check_allowed, package_exception
+from . import fastpickle
 
 SHUTDOWN = b"__KTB_SHUTDOWN__"
 
@@ -193,7 +194,7 @@ def worker_main(conn, local_rank: int, pointers, init_args, name: str, max_threa
                         extra = {"res_needed": total}  # arena too small: this reply travels pickled, next one fits
             validate_result(result, req["serialization"])
             try:
-                payload = pickle.dumps(result, protocol=5)
+                payload = fastpickle.dumps(result)   # plain CPU tensors as raw bytes (see fastpickle.py)
             except Exception as e:  # noqa: BLE001
                 raise SerializationError(f"Result could not be serialized with pickle: {e}")
             reply({"id": req["id"], "ok": True, "result": payload, **extra})

@@ -19,6 +19,7 @@ from typing import Any, Dict, List, Optional
 
 from ..distributed import local_pod_ips
 from .codec import HTTPException, check_allowed, package_exception, rebuild_exception
+from . import fastpickle
 from .process_pool import ProcessPool
 from .process_worker import instantiate, load_callable, resolve_method, validate_result
 
@@ -227,7 +228,7 @@ class SPMDSupervisor:
             self.cleanup()
             self.setup()
         ranks = [n * self.num_proc + l for n in nodes for l in range(self.num_proc)]
-        payload = pickle.dumps((params.get("args", []), params.get("kwargs", {})), protocol=5)  # once for all ranks
+        payload = fastpickle.dumps((params.get("args", []), params.get("kwargs", {})))  # once for all ranks
         envs = self.rank_envs()
         futures = self.pool.call_all(payload, method_name, envs, serialization, ranks=ranks)
         done, _ = wait(futures, return_when=FIRST_EXCEPTION)

@@ -400,3 +400,34 @@ def test_endpoint_must_name_the_deployed_callable():
         assert ei.value.status_code == 404
     finally:
         f.teardown()
+
+
+def test_fastpickle_roundtrips_and_sends_only_addressed_bytes():
+    """Pipes between coordinator and ranks: plain CPU tensors travel as (dtype, shape, raw bytes); everything else
+    takes the stock reduction.  A view must not drag its whole storage along."""
+    import pickle
+
+    from kubetorch_b200.serving import fastpickle as F
+
+    big = torch.randn(1 << 18)
+    objs = [torch.randn(256), torch.randn(7, 3).bfloat16(), torch.tensor(3.5), torch.empty(0, 4), big[5:261],
+            torch.randn(4, 5).t(), torch.randint(0, 2, (9,)).bool(), torch.randn(5).half(),
+            torch.randn(3, requires_grad=True), torch.nn.Parameter(torch.randn(2)),
+            {"a": [torch.ones(2), ("x", torch.zeros(1, dtype=torch.int64))], "b": 5, "c": None}]
+
+    def same(a, b):
+        if isinstance(a, torch.Tensor):
+            return type(a) is type(b) and a.dtype == b.dtype and a.shape == b.shape and \
+                a.requires_grad == b.requires_grad and torch.equal(a, b)
+        if isinstance(a, dict):
+            return a.keys() == b.keys() and all(same(a[k], b[k]) for k in a)
+        if isinstance(a, (list, tuple)):
+            return type(a) is type(b) and len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+        return a == b
+
+    for o in objs:
+        assert same(o, F.loads(F.dumps(o)))
+    assert len(F.dumps(big[5:261])) < 2048 < len(pickle.dumps(big[5:261]))
+    got = F.loads(F.dumps(torch.zeros(4)))
+    got += 1  # results are writable tensors
+    assert got.tolist() == [1.0] * 4
