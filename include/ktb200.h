@@ -234,10 +234,13 @@ int ktb_map_host_multi(int op, int dtype, const void* src_host, void* dst_host, 
 /* ---- bf16 MLP policy (BASELINE config C4) ---------------------------------------------------------- */
 
 /* logits[M,d_out] = W3·relu(W2·relu(W1·obs^T)) with bf16 storage, fp32 accumulation on tcgen05
- * tensor cores, activations rounded to bf16 between layers.  W_l is [d_l, d_{l-1}] row-major
- * (nn.Linear layout).  Requires M % 128 == 0, d_in % 64 == 0, d_hidden % 128 == 0,
- * d_out % 16 == 0 and d_out <= 256.  `scratch` holds 2*M_chunk*d_hidden bf16 (see
- * ktb_mlp_scratch_bytes). */
+ * tensor cores (TMEM accumulators, TMA-fed CTA pairs), activations rounded to bf16 between layers.
+ * W_l is [d_l, d_{l-1}] row-major (nn.Linear layout).  This build: M % 128 == 0, d_in % 64 == 0,
+ * d_hidden % 256 == 0, d_out == 64 (KTB_ERR_UNSUPPORTED otherwise).  Rows are processed in chunks;
+ * for chunks with rows % 256 == 0 layer 2 and the head run as ONE kernel (the second hidden activation
+ * never leaves the SM), other chunks use three GEMM launches — results agree within one bf16 ulp.
+ * `scratch` holds 2*M_chunk*d_hidden bf16 (see ktb_mlp_scratch_bytes).  Replaces the user's
+ * nn.Sequential policy inside execute_callable_async (kt/serving/http_server.py:1845-1891). */
 size_t ktb_mlp_scratch_bytes(size_t M, int d_hidden);
 int ktb_mlp_bf16(int dev, const void* obs, size_t M, int d_in, int d_hidden, int d_out,
                  const void* W1, const void* W2, const void* W3, void* logits, void* scratch,
