@@ -29,7 +29,8 @@ from .exceptions import (  # noqa: F401
 from .mapped import mapped, mapped_spec  # noqa: F401
 from .resources.callables import Cls, Fn, Module, cls, fn  # noqa: F401
 from .resources.compute import Compute  # noqa: F401
-from .resources.decorators import async_, compute, distribute  # noqa: F401
+from .resources.decorators import async_, autoscale, compute, distribute  # noqa: F401
+from .resources.inert import Image, Secret, Volume, images, secret  # noqa: F401  (call-site stand-ins, see inert.py)
 
 for _exc in EXCEPTION_REGISTRY.values():
     _exc.__module__ = "kubetorch_b200"

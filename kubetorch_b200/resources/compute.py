@@ -66,6 +66,9 @@ class Compute:
         self.service_template = service_template
         self.tolerations = tolerations
         self.env_vars = dict(env_vars or {})
+        if image is not None and getattr(image, "env_vars", None):
+            # Image.set_env_vars is the one image setting with a local meaning: exported to the rank processes
+            self.env_vars = {**image.env_vars, **self.env_vars}
         self.secrets = secrets or []
         self.freeze = freeze
         self.kubeconfig_path = kubeconfig_path

@@ -41,3 +41,16 @@ def async_(obj):
     mod = _as_module(obj)
     mod.async_ = True
     return mod
+
+
+def autoscale(**kwargs):
+    """@kt.autoscale (kt/resources/compute/decorators.py): Knative autoscaling has no meaning on a fixed set of local
+    GPUs; the decorator raises the same error Compute.autoscale() does, at decoration time."""
+    def deco(obj):
+        mod = _as_module(obj)
+        if mod.compute is None:
+            raise ValueError("@kt.autoscale must be applied above @kt.compute")
+        mod.compute.autoscale(**kwargs)
+        return mod
+
+    return deco

@@ -60,6 +60,10 @@ def env_report():
     return {k: os.environ.get(k) for k in keys}
 
 
+def env_get(name):
+    return os.environ.get(name)
+
+
 def raise_value_error(msg):
     raise ValueError(msg)
 

@@ -320,6 +320,27 @@ def test_compute_and_distribute_config_surface():
         assert name in kt.EXCEPTION_REGISTRY and kt.EXCEPTION_REGISTRY[name].__module__ == "kubetorch_b200"
 
 
+def test_cluster_side_resources_are_accepted_at_call_sites():
+    """Programs written against the reference construct images / secrets / volumes next to their compute; on the local
+    route they are inert, except Image.set_env_vars which reaches the rank processes."""
+    img = kt.images.Debian().pip_install(["pytest", "fastapi"]).set_env_vars({"KTB_TEST_FLAG": "from-image"})
+    assert isinstance(img, kt.Image) and img.steps == [("pip_install", ["pytest", "fastapi"])]
+    assert kt.images.Python312().image_id == "python:3.12-slim" and kt.images.pytorch().name == "pytorch2312py3"
+    comp = kt.Compute(cpus=".01", gpu_anti_affinity=True, launch_timeout=300, image=img, secrets=[kt.secret(name="hf")],
+                      volumes=[kt.Volume(name="data", size="1Gi", mount_path="/data")], env_vars={"OTHER": "1"})
+    assert comp.env_vars == {"KTB_TEST_FLAG": "from-image", "OTHER": "1"}
+    with pytest.raises(ValueError, match="Either name or provider"):
+        kt.secret()
+    with pytest.raises(NotImplementedError):
+        comp.autoscale(min_scale=1)
+
+    f = kt.fn(cases.env_get, name="img-env").to(comp.distribute("spmd", workers=1, num_proc=2))
+    try:
+        assert f("KTB_TEST_FLAG") == ["from-image"] * 2 and f("OTHER") == ["1", "1"]
+    finally:
+        f.teardown()
+
+
 def test_config_precedence_setter_env_file_default(tmp_path, monkeypatch):
     """kt/config.py:13-25,76-95: explicit setter > KT_* env > ~/.kt/config.yaml > default."""
     from kubetorch_b200.config import KubetorchConfig
