@@ -430,6 +430,39 @@ def run_ours(args):
         assert torch.equal(o[0], xs[0] * 2)
         r1.teardown()
 
+    # ---- config C4 on one GPU (bf16 policy MLP 256->1024->1024->64 on tcgen05), auxiliary line item, N=1 only ---------
+    mlp_aux = None
+    if rank == 0 and n_gpus == 1:
+        try:
+            from kubetorch_b200.device import mlp as _mlp
+
+            gen = torch.Generator(device="cuda:0").manual_seed(0)
+            w1 = (torch.randn(1024, 256, device="cuda:0", generator=gen) * 0.02).bfloat16()
+            w2 = (torch.randn(1024, 1024, device="cuda:0", generator=gen) * 0.02).bfloat16()
+            w3 = (torch.randn(64, 1024, device="cuda:0", generator=gen) * 0.02).bfloat16()
+            rows = 262144
+            obs = torch.randn(rows, 256, device="cuda:0", generator=gen).bfloat16()
+            logits = torch.empty(rows, 64, dtype=torch.bfloat16, device="cuda:0")
+            for _ in range(3):
+                _mlp.mlp_forward(obs, w1, w2, w3, out=logits)
+            torch.cuda.synchronize()
+            a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(10):
+                _mlp.mlp_forward(obs, w1, w2, w3, out=logits)
+            b2.record()
+            torch.cuda.synchronize()
+            ms_mlp = a.elapsed_time(b2) / 10
+            ref = torch.relu(torch.relu(obs[:4096] @ w1.t()) @ w2.t()) @ w3.t()
+            err = (logits[:4096].float() - ref.float()).abs().max().item()
+            flop = 2 * (256 * 1024 + 1024 * 1024 + 1024 * 64) * rows
+            mlp_aux = {"workload": "configs[3] on one GPU: 262144 states through the bf16 policy MLP", "ms": ms_mlp,
+                       "tflops": flop / ms_mlp / 1e9, "max_abs_diff_vs_torch_bf16_chain_first_4096_rows": err,
+                       "kernels": "gemm_bf16_tn_2sm_kernel (layer 1) + mlp_l2_head_fused_kernel (layer 2 + head)"}
+            del obs, logits, w1, w2, w3
+        except Exception as e:  # noqa: BLE001 - auxiliary: never fails the headline measurement
+            mlp_aux = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     # ---- CPU baseline (N=1 only), bounded sample ---------------------------------------------------------------------
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
@@ -451,7 +484,7 @@ def run_ours(args):
                 "transfer": best_mode, "ms_per_step_by_transfer": modes,
                 "l2": "inputs+outputs (512 MiB) exceed the 126 MB L2; no flush needed",
             },
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "small_calls": small,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "small_calls": small, "c4_mlp_1gpu": mlp_aux,
             "gpu_launches": gpu_launches,
         }
         print(json.dumps(line), flush=True)
