@@ -2,6 +2,7 @@
 import ctypes
 import json
 
+import pytest
 import torch
 from hypothesis import given, settings
 from hypothesis import strategies as st
@@ -76,3 +77,57 @@ def test_error_envelope_and_status_map_agree_with_the_oracle(exc_type, msg):
     assert (env["error_type"], env["message"]) == (ref_env["error_type"], ref_env["message"])
     back = codec.rebuild_exception(env)
     assert isinstance(back, exc_type) and back.pod_name == "p" and "Traceback" in back.remote_traceback
+
+
+worker_item = st.one_of(st.integers(-2, 6), st.sampled_from(["0", "1", "2", "10", "10.0.0.1", "10.0.0.2", "10.0.0.9", "x"]),
+                        st.floats(0, 3))
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.integers(1, 4), st.one_of(st.none(), st.sampled_from(["any", "ready", "0.2", "10.0.0", "zzz"]),
+                                    st.lists(worker_item, min_size=1, max_size=4)))
+def test_worker_selection_agrees_with_the_oracle(n_nodes, workers_arg):
+    """Product: node indices that take part (serving/supervisors.py). Oracle: (remote ips, call_local) of the
+    coordinator (spmd_supervisor.py:219-261). Same participants, same error text."""
+    from kubetorch_b200.serving.supervisors import select_worker_nodes
+
+    ips = [f"10.0.0.{i + 1}" for i in range(n_nodes)]
+    try:
+        remote, local = R.select_workers(workers_arg, ips, ips[0])
+        want = sorted(([0] if local else []) + [ips.index(ip) for ip in remote])
+        err = None
+    except ValueError as e:
+        want, err = None, str(e)
+    if err is not None:
+        with pytest.raises(ValueError) as ei:
+            select_worker_nodes(workers_arg, ips, ips[0])
+        assert str(ei.value) == err
+    else:
+        assert select_worker_nodes(workers_arg, ips, ips[0]) == want
+
+
+tensor_dtypes = st.sampled_from([torch.float32, torch.bfloat16, torch.float16, torch.int64, torch.int32, torch.uint8,
+                                 torch.bool, torch.float64])
+
+
+@settings(max_examples=120, deadline=None)
+@given(tensor_dtypes, st.lists(st.integers(0, 7), min_size=0, max_size=3), st.integers(0, 3), st.booleans())
+def test_fastpickle_equals_stock_pickle_on_tensors(dtype, shape, offset, transpose):
+    """The pipe codec must hand the rank exactly what stock pickle would (dtype, shape, values), for views too."""
+    import pickle
+
+    from kubetorch_b200.serving import fastpickle as F
+
+    n = 1
+    for d in shape:
+        n *= d
+    base = (torch.arange(n + offset) % 5).to(dtype)
+    t = base[offset:].reshape(shape)
+    if transpose and t.dim() >= 2:
+        t = t.transpose(0, 1)
+    payload = {"x": [t, 3], "y": ("s", t[:0] if t.dim() else t)}
+    a = F.loads(F.dumps(payload))
+    b = pickle.loads(pickle.dumps(payload))
+    for got, want in ((a["x"][0], b["x"][0]), (a["y"][1], b["y"][1])):
+        assert got.dtype == want.dtype and got.shape == want.shape and torch.equal(got, want)
+    assert a["x"][1] == 3 and a["y"][0] == "s"
