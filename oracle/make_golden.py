@@ -145,6 +145,12 @@ MULTIPOD_GROUPS = {
         ("mp_env_workers_any", None, [], {"workers": "any"}, "json"),
         ("mp_env_workers_bad", None, [], {"workers": [10]}, "json"),
     ]),
+    "mp_raise_2x2": ("raise_value_error", {"distribution_type": "spmd", "num_proc": 2, "quorum_workers": 2}, 2, [
+        ("mp_raise_value_error", None, ["boom across pods"], {}, "json"),
+    ]),
+    "mp_all_reduce_2x2": ("all_reduce_rank", {"distribution_type": "pytorch", "num_proc": 2, "quorum_workers": 2}, 2, [
+        ("mp_all_reduce_rank_2x2", None, [], {}, "json"),     # gloo group spanning both pods: 0+1+2+3
+    ]),
     "mp_double_2x2": ("double", {"distribution_type": "spmd", "num_proc": 2, "quorum_workers": 2}, 2, [
         ("mp_double_f32_1003_2x2", None, ["@f32_1003"], {}, "pickle"),
         ("mp_double_f32_1003_workers_1", None, ["@f32_1003"], {"workers": [1]}, "pickle"),

@@ -83,7 +83,7 @@ def test_recorded_reference_runtime_through_api(golden, deployed):
             "env_pytorch_4", "workers_any", "env_spmd_2"}  # POD_IPS/MASTER_ADDR are 127.0.0.x here, checked below
     n = 0
     for name, rec in golden["cases"].items():
-        if name in skip or name.startswith(("mlp_", "number_state_", "torch_ddp_", "all_reduce_")):
+        if name in skip or name.startswith(("mlp_", "number_state_", "torch_ddp_", "all_reduce_", "mp_all_reduce_")):
             continue  # the last three groups are replayed by test_recorded_process_groups_and_class_state
         mod = deployed(rec["callable"], rec["distributed_config"], rec["allowed"])
         args = resolve_args(golden, rec["args"])
@@ -109,9 +109,12 @@ def test_recorded_process_groups_and_class_state(golden):
         comp = kt.Compute(cpus="1", allowed_serialization=rec["allowed"].split(","))
         # own rendezvous port: other deployments of this module may still hold the default 12345
         extra = {"port": 29541} if cfg["distribution_type"] == "pytorch" else {}
-        return mod.to(comp.distribute(cfg["distribution_type"], workers=1, num_proc=cfg["num_proc"], **extra))
+        return mod.to(comp.distribute(cfg["distribution_type"], workers=cfg.get("quorum_workers", 1),
+                                      num_proc=cfg["num_proc"], **extra))
 
-    for group in (("torch_ddp_valid_recorded", "torch_ddp_invalid_recorded"), ("all_reduce_rank_pt4",)):
+    # the last record was taken on TWO real pods x 2 ranks: one gloo group spanning both (here: two emulated nodes)
+    for group in (("torch_ddp_valid_recorded", "torch_ddp_invalid_recorded"), ("all_reduce_rank_pt4",),
+                  ("mp_all_reduce_rank_2x2",)):
         mod = fresh(golden["cases"][group[0]], f"pg-{group[0]}")
         try:
             for name in group:

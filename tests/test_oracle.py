@@ -70,7 +70,7 @@ def test_oracle_matches_recorded_reference_runtime(golden):
     n = 0
     for name, rec in golden["cases"].items():
         args = resolve_args(golden, rec["args"])
-        if name == "number_count" or name.startswith(("number_state_", "torch_ddp_", "all_reduce_")):
+        if name == "number_count" or name.startswith(("number_state_", "torch_ddp_", "all_reduce_", "mp_all_reduce_")):
             continue  # call history of one deployment / real torch.distributed ranks: replayed in test_api_cpu.py
         if rec["status_code"] == 200:
             got = _run_oracle(rec, args)
