@@ -33,7 +33,7 @@ if which in ("all", "gemm"):
     w1 = (torch.randn(1024, 256, device="cuda", generator=g) * 0.02).bfloat16()
     w2 = (torch.randn(1024, 1024, device="cuda", generator=g) * 0.02).bfloat16()
     w3 = (torch.randn(64, 1024, device="cuda", generator=g) * 0.02).bfloat16()
-    obs = torch.randn(32768, 256, device="cuda", generator=g).bfloat16()
+    obs = torch.randn(75776, 256, device="cuda", generator=g).bfloat16()   # one default chunk: 4 waves of 74 CTA pairs
     for _ in range(3):
         mlp.mlp_forward(obs, w1, w2, w3)
 torch.cuda.synchronize()
