@@ -9,7 +9,9 @@ Parity pinning: this restatement is checked (tests/test_oracle.py) against
     tests/golden/reference_assets.json with file:line provenance), and
   * outputs of the UNMODIFIED reference pod runtime run in the authoring container by
     oracle/make_golden.py (FastAPI TestClient → supervisors → spawned ProcessWorkers),
-    committed as tests/golden/ref_runtime_*.{json,pt}.
+    committed as tests/golden/ref_runtime.pt: 46 calls on one pod (incl. real gloo DDP / all_reduce ranks) and 10
+    calls on TWO real uvicorn pods (127.0.0.1 / 127.0.0.2 x 2 ranks) for the cross-pod half of the path.
+Fairness of the timed port: oracle/time_reference.py times the unmodified reference beside OracleRuntime.
 
 Functions and the reference code they follow ("kt/" = python_client/kubetorch/):
   serialize_body          kt/serving/utils.py:730-749      (_serialize_body)
@@ -23,6 +25,9 @@ Functions and the reference code they follow ("kt/" = python_client/kubetorch/):
   select_workers          kt/serving/spmd/spmd_supervisor.py:219-261
   spmd_call               kt/serving/spmd/spmd_supervisor.py:103-570 + process_pool.py:125-234
                           + process_worker.py:109-186 (single pod, P local ranks)
+  multipod_call           the coordinator of K pods in the flat topology: spmd_supervisor.py:126-170,219-276,557
+                          + remote_worker_pool.py:254-316 (pinned by the two-pod recordings)
+  tree_children / fanout_targets   spmd_supervisor.py:68-101 (get_tree_children; pinned by recorded outputs)
   local_call              kt/serving/execution_supervisor.py:105-157 (proc idx 0, bare result)
   OracleRuntime           the same path with real spawned worker processes and queues, used as
                           the timed CPU baseline ("port" kind)
