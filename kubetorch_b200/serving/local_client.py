@@ -19,6 +19,21 @@ from .codec import MAGIC_CALL_KWARGS, SERIALIZATION_FORMATS, package_exception, 
 from .supervisors import Request
 
 
+# values a JSON round trip returns unchanged (exact types: a bool is not "an int" here, subclasses are not assumed)
+_JSON_SCALARS = frozenset((str, int, float, bool, type(None)))
+
+
+def _json_invariant(args, kwargs) -> bool:
+    """True when json.loads(json.dumps(...)) would hand back equal objects: only top-level scalars."""
+    for v in args:
+        if type(v) not in _JSON_SCALARS:
+            return False
+    for v in kwargs.values():
+        if type(v) not in _JSON_SCALARS:
+            return False
+    return True
+
+
 def parse_endpoint(endpoint: str):
     """'local://<service>/<callable>[/<method>]' → (callable, method)."""
     path = endpoint.split("://", 1)[-1]
@@ -49,7 +64,7 @@ class LocalClient:
             if magic in kwargs:
                 body[magic] = kwargs.pop(magic)
         body["kwargs"] = kwargs
-        if serialization == "json":
+        if serialization == "json" and not _json_invariant(body.get("args", ()), kwargs):
             try:  # what httpx(json=...) would do to the args on the way out
                 wire = json.loads(json.dumps({"args": body.get("args", []), "kwargs": kwargs}))
             except (TypeError, ValueError) as e:
@@ -63,7 +78,7 @@ class LocalClient:
             if hasattr(e, "remote_traceback"):
                 raise  # already packaged by a rank process
             raise rebuild_exception(package_exception(e, pod_name=self.pod_name)) from None
-        if serialization == "json":
+        if serialization == "json" and type(result) not in _JSON_SCALARS:
             result = json.loads(json.dumps(result))
         return result
 
