@@ -99,6 +99,14 @@ int ktb_arena_free(int dev, void* ptr);
 /* Pinned, device-mapped host memory (portable across registered devices). */
 int ktb_host_alloc(size_t nbytes, void** out);
 int ktb_host_free(void* ptr);
+/* NUMA node of a registered device (sysfs, via its PCI bus id), or -1 if unknown. */
+int ktb_device_numa_node(int dev);
+/* Pinned host block whose byte range (part_end[i-1], part_end[i]] is FIRST-TOUCHED on the NUMA node of
+ * device part_dev[i] (by that device's issue thread) before the block is page-locked (cudaHostRegister,
+ * portable + mapped), so shard i's DMA never crosses the socket interconnect.  n_parts == 0 → plain block.
+ * Replaces the client-side argument/result buffers of kt/serving/http_client.py:1041-1111. */
+int ktb_host_alloc_sharded(size_t nbytes, int n_parts, const size_t* part_end, const int* part_dev, void** out);
+int ktb_host_free_sharded(void* ptr);
 /* CUDA IPC for process-per-rank workers (the reference's ProcessWorker model,
  * kt/serving/process_worker.py:15-60).  `ptr` must be the base of a ktb_arena_alloc block. */
 #define KTB_IPC_HANDLE_BYTES 64
@@ -223,10 +231,10 @@ int ktb_push_status(int dev, const void* ctrl, unsigned int* out);
 int ktb_map_host(int dev, int op, int dtype, const void* src_host, void* dst_host, size_t n_elems,
                  double alpha, double beta, size_t chunk_bytes, void* stage_in, void* stage_out);
 
-/* The same for a sharded call on n_ranks DISTINCT devices, driven from one host thread: rank r's
- * `x.chunk(n_ranks)[r]` (granule as in ktb_scatter_map_gather) moves host → devs[r] → host over that GPU's
- * own PCIe link; chunks are issued chunk-major so all links start at once.  stage_in[r] / stage_out[r]
- * are device buffers of >= 2*chunk_bytes on devs[r].  Synchronous. */
+/* The same for a sharded call on n_ranks DISTINCT devices: rank r's `x.chunk(n_ranks)[r]` (granule as in
+ * ktb_scatter_map_gather) moves host → devs[r] → host over that GPU's own PCIe link, each pipeline enqueued by a
+ * persistent library issue thread bound to the CPUs of that GPU's NUMA node (all links run concurrently).
+ * stage_in[r] / stage_out[r] are device buffers of >= 2*chunk_bytes on devs[r].  Synchronous. */
 int ktb_map_host_multi(int op, int dtype, const void* src_host, void* dst_host, size_t n_elems,
                        size_t granule, double alpha, double beta, int n_ranks, const int* devs,
                        size_t chunk_bytes, void* const* stage_in, void* const* stage_out);

@@ -1,5 +1,5 @@
-// ktb_dispatch.cu — multi-GPU data movement of the remote-map path over NVLink 5 / NVSwitch,
-// and the host-resident (PCIe) form of the call.
+// ktb_dispatch.cu — multi-GPU data movement of the remote-map path over NVLink 5 / NVSwitch
+// (the host-resident PCIe form of the call is ktb_host.cu).
 //
 // Replaces the reference's fan-out/fan-in:
 //   broadcast of the same params to every rank   kt/serving/spmd/spmd_supervisor.py:341,439-455
@@ -266,151 +266,6 @@ int ktb_scatter_map_reduce(int op, int dtype, const void* src_root, size_t n_ele
   return launch_reduce_partials(root_dev, dtype, partials_root, n_ranks, out_root, root_stream);
 }
 
-int ktb_map_host(int dev, int op, int dtype, const void* src_host, void* dst_host, size_t n_elems,
-                 double alpha, double beta, size_t chunk_bytes, void* stage_in, void* stage_out) {
-  int rc = require_device(dev);
-  if (rc) return rc;
-  const size_t es = dtype_size(dtype);
-  KTB_REQUIRE(es != 0, KTB_ERR_ARG, "ktb_map_host: unknown dtype %d", dtype);
-  if (n_elems == 0) return KTB_OK;
-  KTB_REQUIRE(src_host && dst_host && stage_in && stage_out, KTB_ERR_ARG, "ktb_map_host: null argument");
-  KTB_REQUIRE(chunk_bytes >= 4096 && chunk_bytes % 256 == 0, KTB_ERR_ARG,
-              "ktb_map_host: chunk_bytes must be a multiple of 256 and >= 4096 (got %zu)", chunk_bytes);
-  KTB_GUARD(dev);
-  DeviceInfo* di = device_info(dev);
-  const MapParams p = make_params(alpha, beta, dtype);
-  const size_t n_bytes = n_elems * es;
-  const size_t n_chunks = (n_bytes + chunk_bytes - 1) / chunk_bytes;
-  CallEvents events;   // per-call events, destroyed on every exit path
-  cudaEvent_t h2d_done[2], exec_done[2], d2h_done[2];
-  for (int i = 0; i < 2; ++i) {
-    h2d_done[i] = events.make(dev);
-    exec_done[i] = events.make(dev);
-    d2h_done[i] = events.make(dev);
-    KTB_REQUIRE(h2d_done[i] && exec_done[i] && d2h_done[i], KTB_ERR_CUDA, "ktb_map_host: cudaEventCreate failed");
-  }
-  int status = KTB_OK;
-  for (size_t c = 0; c < n_chunks && status == KTB_OK; ++c) {
-    const int b = (int)(c & 1);
-    const size_t off = c * chunk_bytes;
-    const size_t len = std::min(chunk_bytes, n_bytes - off);
-    uint8_t* sin = static_cast<uint8_t*>(stage_in) + (size_t)b * chunk_bytes;
-    uint8_t* sout = static_cast<uint8_t*>(stage_out) + (size_t)b * chunk_bytes;
-    cudaError_t e = cudaSuccess;
-    if (c >= 2) e = cudaStreamWaitEvent(di->stream_h2d, exec_done[b], 0);  // stage_in[b] consumed
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(sin, static_cast<const uint8_t*>(src_host) + off, len, cudaMemcpyHostToDevice,
-                          di->stream_h2d);
-    if (e == cudaSuccess) e = cudaEventRecord(h2d_done[b], di->stream_h2d);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(di->stream_exec, h2d_done[b], 0);
-    if (e == cudaSuccess && c >= 2) e = cudaStreamWaitEvent(di->stream_exec, d2h_done[b], 0);  // stage_out[b] drained
-    if (e == cudaSuccess) {
-      status = launch_map(dev, op, dtype, sin, sout, len / es, p, KTB_VARIANT_AUTO, di->stream_exec);
-      if (status != KTB_OK) break;
-      e = cudaEventRecord(exec_done[b], di->stream_exec);
-    }
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(di->stream_d2h, exec_done[b], 0);
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(static_cast<uint8_t*>(dst_host) + off, sout, len, cudaMemcpyDeviceToHost,
-                          di->stream_d2h);
-    if (e == cudaSuccess) e = cudaEventRecord(d2h_done[b], di->stream_d2h);
-    if (e != cudaSuccess) {
-      set_error("ktb_map_host: chunk %zu failed: %s", c, cudaGetErrorString(e));
-      status = KTB_ERR_CUDA;
-    }
-  }
-  cudaError_t es1 = cudaStreamSynchronize(di->stream_d2h);
-  cudaError_t es2 = cudaStreamSynchronize(di->stream_exec);
-  cudaError_t es3 = cudaStreamSynchronize(di->stream_h2d);
-  if (status == KTB_OK && (es1 != cudaSuccess || es2 != cudaSuccess || es3 != cudaSuccess)) {
-    cudaError_t e = es1 != cudaSuccess ? es1 : (es2 != cudaSuccess ? es2 : es3);
-    set_error("ktb_map_host: stream sync failed: %s", cudaGetErrorString(e));
-    status = KTB_ERR_CUDA;
-  }
-  return status;
-}
-
-int ktb_map_host_multi(int op, int dtype, const void* src_host, void* dst_host, size_t n_elems, size_t granule,
-                       double alpha, double beta, int n_ranks, const int* devs, size_t chunk_bytes,
-                       void* const* stage_in, void* const* stage_out) {
-  const size_t es = dtype_size(dtype);
-  KTB_REQUIRE(es != 0, KTB_ERR_ARG, "ktb_map_host_multi: unknown dtype %d", dtype);
-  KTB_REQUIRE(n_ranks > 0 && n_ranks <= kMaxDevices && devs && stage_in && stage_out, KTB_ERR_ARG,
-              "ktb_map_host_multi: bad rank arguments");
-  if (n_elems == 0) return KTB_OK;
-  KTB_REQUIRE(src_host && dst_host, KTB_ERR_ARG, "ktb_map_host_multi: null host buffer");
-  KTB_REQUIRE(granule > 0 && n_elems % granule == 0, KTB_ERR_ARG, "ktb_map_host_multi: n_elems not a multiple of granule");
-  KTB_REQUIRE(chunk_bytes >= 4096 && chunk_bytes % 256 == 0, KTB_ERR_ARG,
-              "ktb_map_host_multi: chunk_bytes must be a multiple of 256 and >= 4096 (got %zu)", chunk_bytes);
-  for (int r = 0; r < n_ranks; ++r) {
-    int rc = require_device(devs[r]);
-    if (rc) return rc;
-    for (int q = 0; q < r; ++q)
-      KTB_REQUIRE(devs[q] != devs[r], KTB_ERR_ARG, "ktb_map_host_multi: devices must be distinct (use ktb_map_host per rank)");
-    KTB_REQUIRE(stage_in[r] && stage_out[r], KTB_ERR_ARG, "ktb_map_host_multi: rank %d has no staging buffers", r);
-  }
-  static std::mutex host_multi_mu;   // the per-device copy/exec streams and events carry one call at a time
-  std::lock_guard<std::mutex> lk(host_multi_mu);
-  const MapParams p = make_params(alpha, beta, dtype);
-  size_t sb[kMaxDevices], sbytes[kMaxDevices], max_chunks = 0;
-  for (int r = 0; r < n_ranks; ++r) {
-    size_t b = 0, e = 0;
-    ktb_shard_bounds(n_elems / granule, n_ranks, r, &b, &e);
-    sb[r] = b * granule * es;
-    sbytes[r] = (e - b) * granule * es;
-    max_chunks = std::max(max_chunks, (sbytes[r] + chunk_bytes - 1) / chunk_bytes);
-  }
-  int status = KTB_OK;
-  // chunk-major issue order: every GPU's PCIe link starts moving data before any link gets its second chunk
-  for (size_t c = 0; c < max_chunks && status == KTB_OK; ++c) {
-    for (int r = 0; r < n_ranks && status == KTB_OK; ++r) {
-      const size_t off = c * chunk_bytes;
-      if (off >= sbytes[r]) continue;
-      const int dev = devs[r];
-      KTB_GUARD(dev);
-      DeviceInfo* di = device_info(dev);
-      const int b = (int)(c & 1);
-      cudaEvent_t h2d_done = di->host_ev[b], exec_done = di->host_ev[2 + b], d2h_done = di->host_ev[4 + b];
-      const size_t len = std::min(chunk_bytes, sbytes[r] - off);
-      uint8_t* sin = static_cast<uint8_t*>(stage_in[r]) + (size_t)b * chunk_bytes;
-      uint8_t* sout = static_cast<uint8_t*>(stage_out[r]) + (size_t)b * chunk_bytes;
-      cudaError_t e = cudaSuccess;
-      if (c >= 2) e = cudaStreamWaitEvent(di->stream_h2d, exec_done, 0);
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(sin, static_cast<const uint8_t*>(src_host) + sb[r] + off, len, cudaMemcpyHostToDevice,
-                            di->stream_h2d);
-      if (e == cudaSuccess) e = cudaEventRecord(h2d_done, di->stream_h2d);
-      if (e == cudaSuccess) e = cudaStreamWaitEvent(di->stream_exec, h2d_done, 0);
-      if (e == cudaSuccess && c >= 2) e = cudaStreamWaitEvent(di->stream_exec, d2h_done, 0);
-      if (e == cudaSuccess) {
-        status = launch_map(dev, op, dtype, sin, sout, len / es, p, KTB_VARIANT_AUTO, di->stream_exec);
-        if (status != KTB_OK) break;
-        e = cudaEventRecord(exec_done, di->stream_exec);
-      }
-      if (e == cudaSuccess) e = cudaStreamWaitEvent(di->stream_d2h, exec_done, 0);
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(static_cast<uint8_t*>(dst_host) + sb[r] + off, sout, len, cudaMemcpyDeviceToHost,
-                            di->stream_d2h);
-      if (e == cudaSuccess) e = cudaEventRecord(d2h_done, di->stream_d2h);
-      if (e != cudaSuccess) {
-        set_error("ktb_map_host_multi: rank %d chunk %zu failed: %s", r, c, cudaGetErrorString(e));
-        status = KTB_ERR_CUDA;
-      }
-    }
-  }
-  for (int r = 0; r < n_ranks; ++r) {
-    DeviceGuard g(devs[r]);
-    DeviceInfo* di = device_info(devs[r]);
-    cudaError_t e1 = cudaStreamSynchronize(di->stream_d2h);
-    cudaError_t e2 = cudaStreamSynchronize(di->stream_exec);
-    cudaError_t e3 = cudaStreamSynchronize(di->stream_h2d);
-    if (status == KTB_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)) {
-      cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
-      set_error("ktb_map_host_multi: stream sync on device %d failed: %s", devs[r], cudaGetErrorString(e));
-      status = KTB_ERR_CUDA;
-    }
-  }
-  return status;
-}
+// ktb_map_host / ktb_map_host_multi (host-resident args over PCIe) live in ktb_host.cu.
 
 }  // extern "C"

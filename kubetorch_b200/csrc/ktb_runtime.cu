@@ -21,6 +21,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+const char* last_error_cstr() { return g_err; }
+void host_workers_shutdown();   // ktb_host.cu
+void host_blocks_shutdown();    // ktb_host.cu
+
 static std::mutex g_mu;
 static DeviceInfo g_dev[kMaxDevices];
 static std::atomic<bool> g_registered[kMaxDevices];   // publication flag: set after g_dev[d] is fully built
@@ -115,6 +119,8 @@ int ktb_init(int n_dev, const int* dev_ids) {
 }
 
 int ktb_shutdown(void) {
+  host_workers_shutdown();
+  host_blocks_shutdown();
   std::lock_guard<std::mutex> lk(g_mu);
   for (auto& kv : g_ipc_open) {   // peers' arenas mapped into this process
     if (kv.second >= 0 && kv.second < kMaxDevices && g_dev[kv.second].registered) {

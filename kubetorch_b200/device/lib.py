@@ -47,6 +47,9 @@ _SIGNATURES = {
     "ktb_arena_free": (c_int, [c_int, c_void_p]),
     "ktb_host_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
     "ktb_host_free": (c_int, [c_void_p]),
+    "ktb_device_numa_node": (c_int, [c_int]),
+    "ktb_host_alloc_sharded": (c_int, [c_size_t, c_int, POINTER(c_size_t), POINTER(c_int), POINTER(c_void_p)]),
+    "ktb_host_free_sharded": (c_int, [c_void_p]),
     "ktb_ipc_export": (c_int, [c_int, c_void_p, c_void_p]),
     "ktb_ipc_open": (c_int, [c_int, c_void_p, POINTER(c_void_p)]),
     "ktb_ipc_close": (c_int, [c_int, c_void_p]),

@@ -37,6 +37,31 @@ def require_cuda():
         )
 
 
+def device_count() -> int:
+    return torch.cuda.device_count()
+
+
+def synchronize(device: int) -> None:
+    torch.cuda.synchronize(device)
+
+
+def is_pinned(t: torch.Tensor) -> bool:
+    return (not t.is_cuda) and t.is_pinned()
+
+
+def join_devices(root: int, devices: Sequence[int]) -> None:
+    """Order the root's current stream after everything enqueued so far on the current streams of `devices`."""
+    root_stream = torch.cuda.current_stream(root)
+    for d in set(int(d) for d in devices):
+        if d == root:
+            continue
+        ev = torch.cuda.Event()
+        with torch.cuda.device(d):
+            ev.record(torch.cuda.current_stream(d))
+        with torch.cuda.device(root):
+            root_stream.wait_event(ev)
+
+
 def ensure_init(devices: Sequence[int]) -> None:
     """Register devices with the library (enables NVLink peer access between all registered)."""
     if _registered.issuperset(devices):  # per-call fast path: nothing to register
@@ -502,6 +527,81 @@ class PushSession:
                 raise RuntimeError(f"push pipeline: an in-kernel wait timed out on cuda:{d}")
 
 
+# ---- NUMA-sharded pinned host tensors ------------------------------------------------------------------
+class _PinnedPool:
+    """Recycles ktb_host_alloc_sharded blocks (page-faulting + page-locking 256 MiB costs ~100 ms; a call must not).
+    A block returns to the pool when the last tensor view of it dies (weakref.finalize on the exporting buffer)."""
+
+    MAX_CACHED_BYTES = 8 << 30
+
+    def __init__(self):
+        self._free = {}
+        self._cached = 0
+        self._lock = threading.Lock()
+
+    def take(self, key):
+        with self._lock:
+            lst = self._free.get(key)
+            if lst:
+                self._cached -= key[0]
+                return lst.pop()
+        return None
+
+    def give(self, key, ptr):
+        with self._lock:
+            if self._cached + key[0] <= self.MAX_CACHED_BYTES:
+                self._free.setdefault(key, []).append(ptr)
+                self._cached += key[0]
+                return
+        try:
+            L.call("ktb_host_free_sharded", ctypes.c_void_p(ptr))
+        except Exception:  # noqa: BLE001 - interpreter shutdown / library already closed
+            pass
+
+
+_pinned_pool = _PinnedPool()
+_PINNED_POOL_MIN_BYTES = 4 << 20
+
+
+def pinned_empty(shape, dtype: torch.dtype, devices: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """Uninitialised pinned host tensor.  With `devices` (distinct GPU ids, rank order) and at least 4 MiB, the
+    pages of `x.chunk(len(devices))[r]` sit on the NUMA node of devices[r] (ktb_host_alloc_sharded), so every GPU
+    of a sharded host-resident call moves its shard over its own socket's memory controllers."""
+    import weakref
+
+    shape = tuple(int(s) for s in shape)
+    numel = 1
+    for d in shape:
+        numel *= d
+    es = torch.empty((), dtype=dtype).element_size()
+    nbytes = numel * es
+    devs = [int(d) for d in (devices or [])]
+    if nbytes < _PINNED_POOL_MIN_BYTES or not devs:
+        return torch.empty(shape, dtype=dtype, pin_memory=True)
+    ensure_init(set(devs))
+    if len(set(devs)) != len(devs) or len(devs) == 1:
+        devs, part_end = devs[:1], [nbytes]
+    else:
+        rows = shape[0] if shape else 1
+        gran = numel // max(rows, 1)
+        part_end = [shard_bounds(rows, len(devs), r)[1] * gran * es for r in range(len(devs))]
+    key = (nbytes, tuple(devs), tuple(part_end))
+    ptr = _pinned_pool.take(key)
+    if ptr is None:
+        out = ctypes.c_void_p()
+        L.call("ktb_host_alloc_sharded", nbytes, len(devs), L.arr(ctypes.c_size_t, part_end), L.arr(ctypes.c_int, devs),
+               ctypes.byref(out))
+        ptr = out.value
+    buf = (ctypes.c_uint8 * nbytes).from_address(ptr)
+    weakref.finalize(buf, _pinned_pool.give, key, ptr)
+    return torch.frombuffer(buf, dtype=torch.uint8).view(dtype).reshape(shape)
+
+
+def device_numa_node(device: int) -> int:
+    ensure_init({device})
+    return L.load().ktb_device_numa_node(int(device))
+
+
 # ---- host-resident args ------------------------------------------------------------------------------
 _stage_cache = {}
 _host_locks = {}
@@ -549,8 +649,8 @@ _multi_lock = threading.Lock()
 
 
 def host_chunk_bytes(shard_bytes: int) -> int:
-    """Chunk size of the host pipeline: ~4 chunks per shard, between 1 MiB and 16 MiB, 256-byte multiple."""
-    c = max(1 << 20, min(16 << 20, shard_bytes // 4))
+    """Chunk size of the host pipeline: ~8 chunks per shard, between 1 MiB and 8 MiB, 256-byte multiple."""
+    c = max(1 << 20, min(8 << 20, shard_bytes // 8))
     return (c + 255) // 256 * 256
 
 

@@ -188,16 +188,11 @@ class Module:
         use_b200 = dtype == "b200" or (spec is not None and compute.gpus and backend != "cpu"
                                        and dtype in (None, "spmd", "pytorch"))
         if use_b200:
-            if num_proc == "auto":
-                per_worker = None
-            else:
-                per_worker = int(num_proc or compute.gpus or 1)
-            n = None if per_worker is None else workers * per_worker
-            return dict(distribution_type="b200", callable_obj=target, num_proc=n, distributed=bool(dist),
-                        devices=dist.get("devices") if dist else None,
-                        transfer=(dist.get("transfer", "auto") if dist else "auto"),
-                        host_mode=(dist.get("host_mode", "multi") if dist else "multi"),
-                        placement=(dist.get("placement", "ranks") if dist else "ranks"), **common)
+            per_worker = None if num_proc in ("auto", None) and not compute.gpus else \
+                (None if num_proc == "auto" else int(num_proc or compute.gpus or 1))
+            extra = {k: dist[k] for k in ("devices", "transfer", "host_mode", "placement", "self_check") if dist and k in dist}
+            return dict(distribution_type="b200", callable_obj=target, num_proc=per_worker, workers=workers,
+                        distributed=bool(dist), **extra, **common)
         if dtype in SPMD_TYPES:
             extra = {k: v for k, v in dist.items()
                      if k not in ("distribution_type", "workers", "quorum_workers", "num_proc", "port",

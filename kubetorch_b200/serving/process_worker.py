@@ -42,6 +42,35 @@ def load_callable(pointers, init_args: Optional[dict]):
     return instantiate(obj, init_args)
 
 
+def load_callable_from_env():
+    """The reference server's loader (kt/serving/http_server.py:1040-1101): KT_FILE_PATH on sys.path, import
+    KT_MODULE_NAME, take KT_CLS_OR_FN_NAME, unwrap deploy decorators, instantiate classes from KT_INIT_ARGS.
+    Used when a supervisor is built the way `load_supervisor` builds it — from KT_DISTRIBUTED_CONFIG alone."""
+    from .codec import HTTPException
+
+    try:
+        name, module_name = os.environ["KT_CLS_OR_FN_NAME"], os.environ["KT_MODULE_NAME"]
+    except KeyError as e:
+        raise RuntimeError(f"{e.args[0]} is not set: no callable metadata to load (deploy with .to() or set KT_* env)")
+    root = os.environ.get("KT_FILE_PATH")
+    if root:
+        root = os.path.abspath(os.path.expanduser(root))
+        if root not in sys.path:
+            sys.path.insert(0, root)
+    module = importlib.import_module(module_name)
+    try:
+        obj = getattr(module, name)
+    except AttributeError as e:
+        raise HTTPException(404, f"Callable '{name}' not found in module '{module_name}'") from e
+    if getattr(obj, "_kt_partial_module", False) and hasattr(obj, "__wrapped__"):
+        obj = obj.__wrapped__
+    init_args = None
+    raw = os.environ.get("KT_INIT_ARGS", "null")
+    if raw not in ("null", "None", ""):
+        init_args = json.loads(raw)
+    return instantiate(obj, init_args)
+
+
 def instantiate(obj, init_args: Optional[dict]):
     """Classes become one instance per rank built from init_args (http_server.py:1088-1101)."""
     if inspect.isclass(obj):
