@@ -1,29 +1,34 @@
-"""User module deployed behind the REFERENCE server in tests/test_b3_seam.py: plain kubetorch-style SPMD
-functions (they shard by RANK/WORLD_SIZE) plus the one new line that declares the device op."""
-import os
+"""User module deployed behind the supervisor seam in tests/test_b3_seam.py (REFERENCE server, CPU stub) and
+tests/test_gpu_api.py::test_b3_* (real kernels): the parity callables of oracle/cases.py — plain kubetorch-style
+SPMD functions that shard by RANK/WORLD_SIZE — plus the ONE new line per function that declares its device op.
+Loaded the way the reference loads user code: by name, from KT_FILE_PATH / KT_MODULE_NAME / KT_CLS_OR_FN_NAME."""
+import functools
+import types
 
 import kubetorch_b200 as ktb
+from oracle import cases
 
 
-def _shard(x):
-    r, w = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    chunks = x.chunk(w)
-    return chunks[r] if r < len(chunks) else x[:0]
+def _mapped(fn, *a, **k):
+    """@ktb.mapped on a COPY of the oracle callable (the shared function object stays undecorated)."""
+    clone = types.FunctionType(fn.__code__, fn.__globals__, fn.__name__, fn.__defaults__, fn.__closure__)
+    clone = functools.update_wrapper(clone, fn)
+    clone.__dict__.pop("__ktb_mapped__", None)
+    del clone.__wrapped__
+    return ktb.mapped(*a, **k)(clone)
+
+
+double = _mapped(cases.double, "scale", alpha=2.0)
+identity = _mapped(cases.identity, "identity")
+scale = _mapped(cases.scale, "scale", alpha="alpha")
+affine = _mapped(cases.affine, "affine", alpha="alpha", beta="beta")
+shard_sum = _mapped(cases.shard_sum, "affine", alpha="alpha", beta="beta", reduce="sum")
 
 
 @ktb.mapped("scale", alpha=2.0)
-def double(x):
-    return _shard(x) * 2
-
-
-@ktb.mapped("affine", alpha="alpha", beta="beta")
-def affine(x, alpha, beta):
-    return _shard(x) * alpha + beta
-
-
-@ktb.mapped("identity", reduce="sum")
-def shard_sum(x):
-    return int(_shard(x).sum())
+def not_really_double(x):
+    """A WRONG declaration (the body triples): the deploy-time self-check must refuse it."""
+    return cases._shard(x) * 3
 
 
 class Scaler:
@@ -34,4 +39,4 @@ class Scaler:
 
     @ktb.mapped("scale", alpha=3.0)
     def triple(self, x):
-        return _shard(x) * 3
+        return cases._shard(x) * 3

@@ -350,3 +350,141 @@ def test_root_placement_option_gives_identical_results():
         assert all(torch.equal(g.cpu(), w) for g, w in zip(got, want))
     finally:
         remote.teardown()
+
+
+# ---- seam B3: the reference's supervisor contract, on the real kernels -------------------------------------------
+def _b3_supervisor(monkeypatch, name, cfg, world, allowed="json,pickle", init_args=None):
+    """Build the supervisor the way the reference's server does (http_server.py:971-1002): from the JSON
+    distributed config alone, with the callable named by the KT_* environment."""
+    import json
+
+    from conftest import REPO
+    from kubetorch_b200.serving.b200_supervisor import B200Supervisor
+
+    monkeypatch.setenv("KT_FILE_PATH", os.path.join(REPO, "tests"))
+    monkeypatch.setenv("KT_MODULE_NAME", "b3_user_module")
+    monkeypatch.setenv("KT_CLS_OR_FN_NAME", name)
+    monkeypatch.setenv("KT_INIT_ARGS", json.dumps(init_args))
+    monkeypatch.setenv("KT_ALLOWED_SERIALIZATION", allowed)
+    monkeypatch.setenv("POD_NAME", "b3-pod")
+    wire_cfg = json.loads(json.dumps({**cfg, "distribution_type": "b200", "devices": [0] * world}))   # JSON values only
+    wire_cfg.pop("distribution_type")
+    sup = B200Supervisor(**wire_cfg)
+    sup.setup()
+    return sup
+
+
+def test_b3_raw_reference_request_bodies_bit_equal_to_recorded_results(golden, monkeypatch):
+    """Every recorded tensor call of the reference runtime, replayed at the supervisor seam: the RAW request body the
+    reference's client produces (`{"data": b64(pickle)}` + hoisted workers) goes into B200Supervisor.call, the return
+    value goes through the reference client's response decoder, and the result must be bit-equal to what the
+    reference's own pods returned."""
+    from kubetorch_b200.serving.supervisors import Request
+
+    names = {"double", "identity", "scale", "affine", "shard_sum"}
+    n = 0
+    for case, rec in golden["cases"].items():
+        if rec["callable"] not in names or rec["serialization"] != "pickle":
+            continue
+        cfg = rec["distributed_config"]
+        pods = len(rec.get("pods") or [None])
+        world = cfg["num_proc"] * pods
+        sup = _b3_supervisor(monkeypatch, rec["callable"], {"num_proc": cfg["num_proc"], "quorum_workers": pods}, world)
+        try:
+            args = resolve_args(golden, rec["args"])
+            body = ref_dispatch.serialize_body(ref_dispatch.build_call_body(*args, **dict(rec.get("kwargs") or {})), "pickle")
+            assert set(body) <= {"data", "workers", "restart_procs"} and isinstance(body["data"], str)
+            raw = sup.call(Request({"X-Serialization": "pickle", "X-Request-ID": case}), rec["callable"], None, body)
+            assert isinstance(raw, list) and all(isinstance(r, dict) and set(r) == {"data"} for r in raw), case
+            got = ref_dispatch.deserialize_response(raw, "pickle")
+            want = rec["result"]
+            assert len(got) == len(want), case
+            for g, w in zip(got, want):
+                if isinstance(w, torch.Tensor):
+                    assert g.dtype == w.dtype and tuple(g.shape) == tuple(w.shape), case
+                    assert torch.equal(g.cpu().reshape(-1).view(torch.uint8), w.reshape(-1).view(torch.uint8)), case
+                elif isinstance(w, float):
+                    x = args[0]
+                    assert abs(g - w) <= 8 * torch.finfo(torch.float32).eps * float(x.float().abs().sum()), case
+                else:
+                    assert g == w, case
+        finally:
+            sup.cleanup()
+        n += 1
+    assert n >= 14
+
+
+def test_b3_workers_restart_and_errors_on_the_device_route(monkeypatch):
+    from kubetorch_b200.serving.supervisors import Request
+
+    req = Request({"X-Serialization": "pickle"})
+    x = torch.arange(1003, dtype=torch.float32)
+    sup = _b3_supervisor(monkeypatch, "double", {"num_proc": 2, "quorum_workers": 2}, 4)
+    try:
+        def call(**magic):
+            body = ref_dispatch.serialize_body(ref_dispatch.build_call_body(x, **magic), "pickle")
+            return ref_dispatch.deserialize_response(sup.call(req, "double", None, body), "pickle")
+
+        full = call()
+        assert [tuple(t.shape) for t in full] == [(251,), (251,), (251,), (250,)]
+        sub = call(workers=[1])                          # node 1 = global ranks 2, 3 (recorded: mp_double_f32_1003_workers_1)
+        assert [tuple(t.shape) for t in sub] == [(251,), (250,)]
+        assert torch.equal(sub[0], x[502:753] * 2) and torch.equal(sub[1], x[753:] * 2)
+        assert len(call(workers=["1"])) == 2 and len(call(workers="any")) == 2 and len(call(workers=[0, 1])) == 4
+        with pytest.raises(ValueError, match=r"Worker index 10 out of range. Valid range: 0-1"):
+            call(workers=[10])
+        with pytest.raises(ValueError, match=r"Invalid worker specification: 1.5. Must be an IP address"):
+            call(workers=[1.5])
+        before = sup._callable
+        assert len(call(restart_procs=True)) == 4 and sup._callable is not None
+        # device-resident args take the same selectors
+        body = {"args": [x.cuda()], "kwargs": {}, "workers": [1]}
+        live = sup.call(req, "double", None, body)          # live objects (LocalClient form): tensors come back live
+        assert [tuple(t.shape) for t in live] == [(251,), (250,)] and live[0].is_cuda
+        torch.cuda.synchronize()
+        assert torch.equal(live[1].cpu(), x[753:] * 2)
+        del before
+    finally:
+        sup.cleanup()
+    # a kt.cls behind the seam: restart_procs re-creates the instance (fresh state)
+    sup = _b3_supervisor(monkeypatch, "Scaler", {"num_proc": 3}, 3, init_args={"tag": "a"})
+    try:
+        inst = sup._callable
+        assert inst.tag == "a"
+        body = ref_dispatch.serialize_body(ref_dispatch.build_call_body(torch.arange(130), restart_procs=True), "pickle")
+        got = ref_dispatch.deserialize_response(sup.call(req, "Scaler", "triple", body), "pickle")
+        assert torch.equal(torch.cat(got), torch.arange(130) * 3) and sup._callable is not inst
+        from kubetorch_b200.serving.codec import HTTPException
+        with pytest.raises(HTTPException, match="Method 'nope' not found in class 'Scaler'"):
+            sup.call(req, "Scaler", "nope", {"args": [], "kwargs": {}})
+    finally:
+        sup.cleanup()
+    # json mode: tensors are not JSON-serialisable (the reference's SerializationError), scalars are
+    sup = _b3_supervisor(monkeypatch, "shard_sum", {"num_proc": 4}, 4)
+    try:
+        xi = torch.arange(130)
+        body = ref_dispatch.serialize_body(ref_dispatch.build_call_body(xi, 1, 0), "pickle")
+        got = ref_dispatch.deserialize_response(sup.call(req, "shard_sum", None, body), "pickle")
+        assert got == [int(c.sum()) for c in xi.chunk(4)]
+        with pytest.raises(TypeError, match="is not an integer"):
+            sup.call(req, "shard_sum", None, {"args": [xi, 0.5, 0], "kwargs": {}})
+    finally:
+        sup.cleanup()
+
+
+def test_mapped_self_check_refuses_a_wrong_declaration(monkeypatch):
+    from kubetorch_b200.serving.b200_supervisor import B200Supervisor
+
+    monkeypatch.setenv("KT_FILE_PATH", os.path.join(os.path.dirname(__file__)))
+    monkeypatch.setenv("KT_MODULE_NAME", "b3_user_module")
+    monkeypatch.setenv("KT_CLS_OR_FN_NAME", "not_really_double")
+    monkeypatch.setenv("KT_INIT_ARGS", "null")
+    sup = B200Supervisor(num_proc=2, devices=[0, 0])
+    with pytest.raises(ValueError, match="self-check failed"):
+        sup.setup()
+    sup.cleanup()
+    import b3_user_module
+
+    remote = kt.fn(b3_user_module.not_really_double, name="t-wrong")
+    with pytest.raises(ValueError, match="self-check failed"):
+        remote.to(kt.Compute(gpus=1).distribute("b200", num_proc=2, devices=[0, 0]))
