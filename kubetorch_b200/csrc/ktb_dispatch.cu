@@ -109,27 +109,28 @@ int ktb_broadcast(int root, const void* src, void* const* dsts, int n_dst, size_
   return KTB_OK;
 }
 
-// Per-call events (created on the device that records them, destroyed right after the waits are enqueued:
-// CUDA releases an event's resources once pending work on it has completed). Shared per-device events would let two
-// host threads using different streams wait on each other's records.
+// Per-THREAD event pool: each host thread owns its events (per device: slot 0 "args ready", slot 1+r "rank r done"), created
+// once and reused by every call the thread makes — a call used to pay N+1 cudaEventCreate/Destroy pairs (≈25 µs at
+// N = 8).  Reuse is safe: cudaStreamWaitEvent captures the record that is current WHEN THE WAIT IS ENQUEUED, so
+// re-recording the event for the next call does not disturb waits enqueued earlier; and because the pool is
+// per thread, two host threads on different streams never see each other's records.
 struct CallEvents {
-  cudaEvent_t ev[kMaxDevices + 1];
-  int dev[kMaxDevices + 1];
-  int n = 0;
-  cudaEvent_t make(int device) {
-    DeviceGuard g(device);
-    cudaEvent_t e = nullptr;
-    if (n > kMaxDevices || !g.ok || cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    ev[n] = e;
-    dev[n] = device;
-    ++n;
-    return e;
-  }
-  ~CallEvents() {
-    for (int i = 0; i < n; ++i) {
-      DeviceGuard g(dev[i]);
-      cudaEventDestroy(ev[i]);
+  cudaEvent_t make(int device, int slot) {
+    struct Pool {
+      cudaEvent_t ev[kMaxDevices][kMaxDevices + 1] = {};
+      ~Pool() {}   // events die with the context at process exit (destroying them here could outlive the driver)
+    };
+    static thread_local Pool pool;
+    if (device < 0 || device >= kMaxDevices || slot < 0 || slot > kMaxDevices) return nullptr;
+    cudaEvent_t& e = pool.ev[device][slot];
+    if (!e) {
+      DeviceGuard g(device);
+      if (!g.ok || cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+        e = nullptr;
+        return nullptr;
+      }
     }
+    return e;
   }
 };
 
@@ -168,7 +169,7 @@ int ktb_scatter_map_gather(int op, int dtype, const void* src_root, void* dst_ro
   cudaStream_t root_stream = stream_of(root_rank);
   CallEvents events;
   cudaEvent_t done[kMaxDevices] = {nullptr};
-  cudaEvent_t args_ready = events.make(root_dev);
+  cudaEvent_t args_ready = events.make(root_dev, 0);
   KTB_REQUIRE(args_ready, KTB_ERR_CUDA, "ktb_scatter_map_gather: cudaEventCreate failed");
   (void)root;
   {
@@ -192,7 +193,7 @@ int ktb_scatter_map_gather(int op, int dtype, const void* src_root, void* dst_ro
                     static_cast<uint8_t*>(dst_root) + b * es, e - b, p, variant, st);
     if (rc) return rc;
     if (!is_root) {
-      done[r] = events.make(dev);
+      done[r] = events.make(dev, 1 + r);
       KTB_REQUIRE(done[r], KTB_ERR_CUDA, "ktb_scatter_map_gather: cudaEventCreate failed");
       KTB_CK(cudaEventRecord(done[r], st));
     }
@@ -230,7 +231,7 @@ int ktb_scatter_map_reduce(int op, int dtype, const void* src_root, size_t n_ele
   cudaStream_t root_stream = stream_of(root_rank);
   CallEvents events;
   cudaEvent_t done[kMaxDevices] = {nullptr};
-  cudaEvent_t args_ready = events.make(root_dev);
+  cudaEvent_t args_ready = events.make(root_dev, 0);
   KTB_REQUIRE(args_ready, KTB_ERR_CUDA, "ktb_scatter_map_reduce: cudaEventCreate failed");
   (void)root;
   {
@@ -255,7 +256,7 @@ int ktb_scatter_map_reduce(int op, int dtype, const void* src_root, size_t n_ele
                            static_cast<uint8_t*>(partials_root) + (size_t)r * acc_size, workspaces[r], st);
     if (rc) return rc;
     if (!is_root) {
-      done[r] = events.make(dev);
+      done[r] = events.make(dev, 1 + r);
       KTB_REQUIRE(done[r], KTB_ERR_CUDA, "ktb_scatter_map_reduce: cudaEventCreate failed");
       KTB_CK(cudaEventRecord(done[r], st));
     }

@@ -128,6 +128,10 @@ __global__ void __launch_bounds__(kPushThreads)
   __shared__ bool flag;
   if (threadIdx.x == 0) flag = spin_until(ready, seq, status);
   __syncthreads();
+  // the piece never arrived (the wait timed out and raised the sticky status word): do NOT map stale staging data
+  // into the caller's result and do NOT acknowledge — the root's wait then times out too and the host maps the
+  // status to PodTerminatedError; the session is torn down, so the unbalanced ticket does not matter
+  if (!flag) return;
   const size_t off = (size_t)blockIdx.x * kPushTile;
   if (off < n_bytes) {
     const size_t len = (n_bytes - off) < (size_t)kPushTile ? (n_bytes - off) : (size_t)kPushTile;

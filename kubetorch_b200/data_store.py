@@ -130,6 +130,8 @@ _groups: Dict[str, _Group] = {}
 # ---- cross-process registry (descriptor files + CUDA IPC arenas) ---------------------------------------------
 _shared_arenas: Dict[str, Any] = {}     # full_key -> Arena owned by this process
 _opened: Dict[str, int] = {}            # handle hex -> mapped device pointer in this process
+_opened_by_key: Dict[str, str] = {}     # full_key -> handle hex this process has mapped for it
+_retired_arenas: List[Any] = []         # outgrown arenas: other processes may still map them, so they are not freed
 
 
 def _store_dir() -> Optional[str]:
@@ -155,9 +157,14 @@ def _publish_shared(full_key: str, t) -> None:
     dev = t.device.index
     nbytes = max(t.numel() * t.element_size(), 1)
     old = _shared_arenas.pop(full_key, None)
-    if old is not None:
-        old.free()
-    arena = ops.Arena(dev, nbytes)
+    if old is not None and old.device == dev and old.nbytes >= nbytes:
+        arena = old              # re-put of the same key: overwrite in place, the exported handle stays valid
+    else:
+        if old is not None:
+            # freeing exported memory that another process still maps is undefined behaviour (CUDA IPC) and there is
+            # no acknowledgement channel between getters and putters: keep it until kt.rm / process exit
+            _retired_arenas.append(old)
+        arena = ops.Arena(dev, nbytes)
     with torch.cuda.device(dev):
         if t.numel():
             ops.map_tensor(t.contiguous().reshape(-1).view(torch.uint8), "identity",
@@ -188,7 +195,15 @@ def _lookup_shared(full_key: str):
     dev = torch.cuda.current_device()
     ptr = _opened.get(desc["handle"])
     if ptr is None:
+        stale = _opened_by_key.get(full_key)
+        if stale is not None and stale in _opened:       # the putter replaced the arena: drop our mapping of the old one
+            torch.cuda.synchronize(dev)
+            try:
+                ops.ipc_close(dev, _opened.pop(stale))
+            except Exception:  # noqa: BLE001
+                pass
         ptr = _opened[desc["handle"]] = ops.ipc_open(dev, bytes.fromhex(desc["handle"]))
+        _opened_by_key[full_key] = desc["handle"]
     holder = type("_CAI", (), {})()
     holder.__cuda_array_interface__ = {"shape": (max(desc["nbytes"], 1),), "typestr": "|u1", "data": (ptr, False),
                                        "version": 3}

@@ -157,6 +157,32 @@ def map_tensor(
     return out
 
 
+def fast_dtype_codes(integral_params: bool) -> dict:
+    """dtype -> code for the small-call lane; integer dtypes only when alpha/beta are integral (torch would promote)."""
+    codes = dict(_DTYPE_CODES)
+    if not integral_params:
+        codes.pop(torch.int32, None)
+        codes.pop(torch.int64, None)
+    return codes
+
+
+def fast_map(device: int, op: str, alpha: float, beta: float):
+    """launch(dtype_code, src_ptr, dst_ptr, n_elems): ONE ctypes hop into ktb_map on torch's current stream of
+    `device`, everything else pre-bound (no per-call marshalling of constants, no Python-level checks)."""
+    ensure_init({device})
+    fn = L.load().ktb_map
+    op_code, dev = OPS[op], int(device)
+    raw = _raw_stream if _raw_stream is not None else (lambda d: torch.cuda.current_stream(d).cuda_stream)
+    check = L.check
+
+    def launch(code, src, dst, n):
+        rc = fn(dev, op_code, code, src, dst, n, alpha, beta, 0, raw(dev))
+        if rc:
+            check(rc)
+
+    return launch
+
+
 _ws_cache = {}
 
 
@@ -470,6 +496,15 @@ def ipc_open(device: int, handle: bytes) -> int:
     return p.value
 
 
+def ipc_close(device: int, ptr: int) -> None:
+    """Unmap an arena opened with ipc_open (must happen before its owner frees it)."""
+    L.call("ktb_ipc_close", int(device), ctypes.c_void_p(ptr))
+
+
+class PushTimeout(RuntimeError):
+    """An in-kernel flag wait of the push/push pipeline timed out (a rank's GPU stalled or died)."""
+
+
 class PushSession:
     """Push/push scatter → exec → gather driven by ONE controller process over distinct GPUs
     (ktb_push_*): the root's kernel pushes shard pieces into each rank's staging buffer, each rank's
@@ -490,11 +525,18 @@ class PushSession:
             torch.cuda.synchronize(d)
         self.seq = 0
         n = len(self.devices)
+        # host mirror of every control block's sticky status word, refreshed by an async D2H copy behind each call:
+        # a timed-out in-kernel wait is seen at the NEXT call without a host sync on the data path
+        self._status_host = torch.zeros(n, dtype=torch.int32).pin_memory()
+        self._status_dev = [c[1032:1036].view(torch.int32) for c in self.ctrl]
         self._stage_ptrs = L.arr(ctypes.c_void_p, [0 if s is None else s.data_ptr() for s in self.stage])
         self._ctrl_ptrs = L.arr(ctypes.c_void_p, [c.data_ptr() for c in self.ctrl])
         self._n = n
 
     def call(self, x_root: torch.Tensor, out_root: torch.Tensor, op: str, alpha: float = 1.0, beta: float = 0.0):
+        if bool(self._status_host.any()):
+            bad = [self.devices[i] for i in self._status_host.nonzero().flatten().tolist()]
+            raise PushTimeout(f"push pipeline: an in-kernel wait timed out on cuda:{bad} during an earlier call")
         self.seq += 1
         seq, n, es = self.seq, self._n, x_root.element_size()
         gran = row_elems(x_root)
@@ -517,6 +559,9 @@ class PushSession:
                    out_root.data_ptr() + b * gran * es, (e - b) * gran, float(alpha), float(beta), L.VARIANT_AUTO,
                    root_stream)
         L.call("ktb_push_wait", self.root, self.ctrl[0].data_ptr(), n, 0, seq, root_stream)
+        for r, d in enumerate(self.devices):   # stream-ordered behind this call's kernels on each device
+            with torch.cuda.device(d):
+                self._status_host[r:r + 1].copy_(self._status_dev[r], non_blocking=True)
         return out_root
 
     def check(self):
@@ -524,7 +569,7 @@ class PushSession:
             st = ctypes.c_uint(0)
             L.call("ktb_push_status", d, c.data_ptr(), ctypes.byref(st))
             if st.value:
-                raise RuntimeError(f"push pipeline: an in-kernel wait timed out on cuda:{d}")
+                raise PushTimeout(f"push pipeline: an in-kernel wait timed out on cuda:{d}")
 
 
 # ---- NUMA-sharded pinned host tensors ------------------------------------------------------------------

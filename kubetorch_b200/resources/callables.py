@@ -81,6 +81,8 @@ class Module:
         self._compute = None
         self._http_client = None
         self._supervisor = None
+        self._fast = None
+        self._fast_sers = frozenset()
         self._serialization = "json"
         self._async = False
         self._get_if_exists = True
@@ -229,6 +231,11 @@ class Module:
         sup.setup()
         self._supervisor = sup
         self._http_client = LocalClient(sup, self.service_name)
+        self._fast = None
+        if hasattr(sup, "fast_path") and self.MODULE_TYPE == "fn":
+            allowed = compute.allowed_serialization_str.split(",")
+            self._fast_sers = frozenset(s for s in ("pickle", "none") if s in allowed)
+            self._fast = sup.fast_path(bool(self._fast_sers))
         _DEPLOYED[self.service_name] = self
         return self
 
@@ -251,6 +258,7 @@ class Module:
             self._supervisor.cleanup()
             self._supervisor = None
         self._http_client = None
+        self._fast = None
         _DEPLOYED.pop(self.service_name, None)
 
     def _client(self, *args, **kwargs):
@@ -280,6 +288,14 @@ class Fn(Module):
     MODULE_TYPE = "fn"
 
     def __call__(self, *args, **kwargs):
+        fast = self._fast
+        if fast is not None and len(args) == 1 and not self._async:
+            # small-call lane: one tensor argument, at most the `serialization` option, a format that may carry tensors
+            if (not kwargs and self._serialization in self._fast_sers) or \
+                    (len(kwargs) == 1 and kwargs.get("serialization") in self._fast_sers):
+                out = fast(args[0])
+                if out is not None:
+                    return out
         async_ = kwargs.pop("async_", self.async_)
         return self._call_async(*args, **kwargs) if async_ else self._call_sync(*args, **kwargs)
 

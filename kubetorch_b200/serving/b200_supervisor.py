@@ -63,7 +63,7 @@ class B200Supervisor:
     def __init__(self, pointers=None, init_args=None, name: str = None, devices: Optional[List[int]] = None,
                  num_proc=None, workers: int = None, quorum_workers: int = None, distributed: bool = True,
                  allowed_serialization: Optional[str] = None, host_chunk_bytes: int = 16 << 20, variant: int = 0,
-                 callable_obj=None, transfer: str = "auto", host_mode: str = "multi", placement: str = "ranks",
+                 callable_obj=None, transfer: str = "auto", host_mode: str = "multi", placement: str = "auto",
                  quorum_timeout=None, monitor_members=None, port=None, restart_procs: bool = True,
                  max_threads_per_proc: int = 10, self_check: bool = True, **extra):
         # (pointers, init_args, name, callable_obj) are the in-package deploy path; the reference's server passes
@@ -90,11 +90,13 @@ class B200Supervisor:
             raise ValueError("transfer must be 'auto', 'pull' or 'push'")
         self.transfer = transfer
         self.host_mode = host_mode  # "multi": one C call drives all GPUs; "threads": one host thread per rank
-        # where device-resident element-wise shards execute: "ranks" = rank r on GPU r (the sharded path the
-        # benchmarks measure); "root" = every rank's shard on the root GPU (same results; for HBM-bound ops a
-        # root-resident arg is served faster by the root's own HBM than through its NVLink port, profiles §2)
-        if placement not in ("ranks", "root"):
-            raise ValueError("placement must be 'ranks' or 'root'")
+        # where device-resident element-wise shards execute: "ranks" = rank r on GPU r whatever the size (the sharded
+        # path the benchmarks measure); "root" = every rank's shard on the root GPU (same results; for HBM-bound ops a
+        # root-resident arg is served faster by the root's own HBM than through its NVLink port, profiles §2);
+        # "auto" (default) = "ranks" from SMALL_CALL_BYTES up, "root" below it (launch-bound calls: one launch
+        # instead of N launches plus 2N peer hops)
+        if placement not in ("auto", "ranks", "root"):
+            raise ValueError("placement must be 'auto', 'ranks' or 'root'")
         self.placement = placement
         self.worker_ips: List[str] = []
         self.config_hash = hash(("b200", tuple(self.devices or ()), num_proc, self.workers, distributed))
@@ -225,6 +227,64 @@ class B200Supervisor:
                         f"the Python body on a seeded {dtype} tensor; refusing to deploy"
                     )
 
+    # ---- small-call lane (the local CUDA-stream scheduler for launch-bound calls) ----------------------------
+    SMALL_CALL_BYTES = 4 << 20
+
+    def fast_path(self, serialization_ok):
+        """A closure `fast(x) -> result | None` for the deployed FUNCTION, or None when there is none.
+
+        The reference pays HTTP + pickle + queue hops per call (≈1 ms); here a small device-resident call is
+        launch-bound, so the per-call host work is cut to: argument checks, one `torch.empty_like`, ONE ctypes hop
+        that binds and launches the kernel on the caller's current stream, and the shard views.  For payloads under
+        SMALL_CALL_BYTES every rank's shard executes on the root GPU in that one launch (the shards of an
+        element-wise op are contiguous in the root's memory; sending 128-byte shards over NVLink to seven other
+        GPUs and back costs more than mapping them where they are) — results are bit-identical to the spread
+        placement.  Anything the lane does not cover returns None and takes the general path (same semantics,
+        same errors)."""
+        import inspect
+
+        import torch
+
+        method = self._callable
+        if not (inspect.isfunction(method) or inspect.ismethod(method)) or not serialization_ok:
+            return None
+        spec = mapped_spec(method)
+        if spec is None or spec.op not in ELEMENTWISE_OPS or spec.reduce is not None:
+            return None
+        if not (isinstance(spec.alpha, (int, float)) and isinstance(spec.beta, (int, float))):
+            return None
+        if len(inspect.signature(method).parameters) != 1 or self.ops is None or not hasattr(self.ops, "fast_map"):
+            return None
+        integral = float(spec.alpha).is_integer() and float(spec.beta).is_integer()
+        world, root, distributed = self.world_size, self.devices[0], self.distributed
+        if self.placement == "ranks" and world > 1 and len(set(self.devices)) == world:
+            return None                      # explicit spread placement: every call fans out, whatever its size
+        spread_ok = self.placement == "auto" and world > 1 and len(set(self.devices)) == world
+        small = self.SMALL_CALL_BYTES
+        launch = self.ops.fast_map(root, spec.op, float(spec.alpha), float(spec.beta))
+        codes = self.ops.fast_dtype_codes(integral)
+        Tensor, empty_like = torch.Tensor, torch.empty_like
+
+        def fast(x):
+            if type(x) is not Tensor or not x.is_cuda:
+                return None
+            code = codes.get(x.dtype)
+            if code is None or x.dim() == 0 or not x.is_contiguous() or x.device.index != root:
+                return None
+            n = x.numel()
+            if n == 0 or (spread_ok and n * x.element_size() >= small) or self._callable is None:
+                return None
+            out = empty_like(x)
+            launch(code, x.data_ptr(), out.data_ptr(), n)
+            if world == 1:
+                return [out] if distributed else out
+            views = list(out.chunk(world))
+            while len(views) < world:          # ranks past the data return an empty shard, like x.chunk(w)[r:r+1]
+                views.append(out[:0])
+            return views
+
+        return fast
+
     # ---- the call ---------------------------------------------------------------------------------------
     def call(self, request, cls_or_fn_name, method_name=None, params=None, distributed_subcall=False):
         serialization = request.headers.get("X-Serialization", "json")
@@ -336,15 +396,15 @@ class B200Supervisor:
             xs, os_ = self._shard_views(x, x, ranks), self._shard_views(out, x, ranks)
             for r, xv, ov in zip(ranks, xs, os_):
                 if xv.numel():
-                    ops.map_tensor(xv, op, alpha, beta, out=ov, device=self.devices[r] if self.placement == "ranks" else root)
+                    ops.map_tensor(xv, op, alpha, beta, out=ov, device=root if self.placement == "root" else self.devices[r])
             ops.join_devices(root, [self.devices[r] for r in ranks])
             return os_
-        if self.placement == "root":
-            ops.scatter_map_gather(x, op, alpha, beta, devices=[root] * len(self.devices), out_root=out,
-                                   variant=self.variant)
+        nbytes = x.numel() * x.element_size()
+        if self.placement == "root" or (self.placement == "auto" and nbytes < self.SMALL_CALL_BYTES):
+            # one launch on the root covers every rank's (contiguous) shard: see fast_path()
+            ops.map_tensor(x, op, alpha, beta, out=out, variant=self.variant)
             return self._shard_views(out, x)
         distinct = len(set(self.devices)) == len(self.devices) and len(self.devices) > 1
-        nbytes = x.numel() * x.element_size()
         # measured crossover (profiles/r1_summary.md §2): the flag pipeline wins from 256 MiB at N >= 4 and from 1 GiB
         # at N = 2; below that the single fused kernel per rank has less fixed cost
         auto_push = distinct and ((len(self.devices) >= 4 and nbytes >= (256 << 20)) or nbytes >= (1 << 30))
@@ -355,23 +415,30 @@ class B200Supervisor:
                 shard_bytes = ops.shard_bounds(rows, self.world_size, 0)[1] * ops.row_elems(x) * x.element_size()
                 if self._push is None or self._push.stride < shard_bytes:
                     self._push = ops.PushSession(self.devices, shard_bytes)
-                self._push.call(x, out, op, alpha, beta)
-                self._push_calls = getattr(self, "_push_calls", 0) + 1
-                if self._push_calls % 64 == 1:
-                    self._check_push()
+                try:
+                    self._push.call(x, out, op, alpha, beta)
+                except ops.PushTimeout as e:
+                    self._push = None
+                    self._raise_device_timeout(e)
         else:
             ops.scatter_map_gather(x, op, alpha, beta, devices=self.devices, out_root=out, variant=self.variant)
         return self._shard_views(out, x)
 
-    def _check_push(self):
+    def _raise_device_timeout(self, e):
         """A timed-out in-kernel wait (a rank's GPU stalled or died) surfaces as the reference's
-        PodTerminatedError (kt/serving/utils.py:111-190), not as silently stale results."""
-        try:
-            self._push.check()
-        except RuntimeError as e:
-            self._push = None
-            raise PodTerminatedError(pod_name=f"{self.name}-0", reason="DeviceTimeout", status_code=503,
-                                     events=[{"reason": "DeviceTimeout", "message": str(e)}]) from None
+        PodTerminatedError (kt/serving/utils.py:111-190), not as silently stale results: the consume kernel skips
+        its stores on a timeout, the status word is mirrored to the host behind every call."""
+        raise PodTerminatedError(pod_name=f"{self.name}-0", reason="DeviceTimeout", status_code=503,
+                                 events=[{"reason": "DeviceTimeout", "message": str(e)}]) from None
+
+    def check_device_health(self):
+        """Synchronous form (reads every control block): used at teardown and by tests."""
+        if self._push is not None:
+            try:
+                self._push.check()
+            except self.ops.PushTimeout as e:
+                self._push = None
+                self._raise_device_timeout(e)
 
     def _pinned(self, key, like):
         buf = self._pin_cache.get(key)

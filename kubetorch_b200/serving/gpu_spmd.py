@@ -35,6 +35,7 @@ class GpuSPMDSupervisor(SPMDSupervisor):
         self.arg_arenas: List = []
         self.res_arenas: List = []
         self._pending_updates: Dict[int, dict] = {}
+        self._retired: List = []          # superseded arenas: freed only after the ranks closed their IPC mappings
         self._call_lock = threading.Lock()
 
     # ---- lifecycle ---------------------------------------------------------------------------------------
@@ -67,7 +68,12 @@ class GpuSPMDSupervisor(SPMDSupervisor):
                 a.free()
             except Exception:  # noqa: BLE001
                 pass
-        self.arg_arenas, self.res_arenas = [], []
+        for _, a in self._retired:
+            try:
+                a.free()
+            except Exception:  # noqa: BLE001
+                pass
+        self.arg_arenas, self.res_arenas, self._retired = [], [], []
         self._pending_updates = {}
         if getattr(self, "_store_dir", None):
             import shutil
@@ -104,9 +110,21 @@ class GpuSPMDSupervisor(SPMDSupervisor):
         torch.cuda.synchronize(self.devices[r])
         old = arenas[r]
         arenas[r] = ops.Arena(self.devices[r], cap)
-        old.free()
+        # freeing exported memory while the rank still maps it is undefined behaviour (CUDA IPC): the rank closes the
+        # old mapping when it receives the update; the free happens after that call's reply (_free_retired)
+        self._retired.append((r, old))
         upd = self._pending_updates.setdefault(r, {})
         upd[f"{which}_handle"], upd[f"{which}_bytes"] = arenas[r].export(), cap
+
+    def _free_retired(self, replied_ranks):
+        """Free superseded arenas whose rank has (a) been sent the new handle and (b) replied since."""
+        keep = []
+        for r, a in self._retired:
+            if r in replied_ranks and r not in self._pending_updates:
+                a.free()
+            else:
+                keep.append((r, a))
+        self._retired = keep
 
     # ---- the call ---------------------------------------------------------------------------------------------
     def call(self, request, cls_or_fn_name, method_name=None, params=None, distributed_subcall=False):
@@ -127,7 +145,10 @@ class GpuSPMDSupervisor(SPMDSupervisor):
         root = self.devices[0]
         leaves: List = []
         use_arenas = torch.cuda.is_available() and serialization != "json"
-        skeleton = split_tensors((args, kwargs), leaves, lambda t: t.is_cuda) if use_arenas else (args, kwargs)
+        # only dtypes the rank-side arena view supports travel through HBM; the rest (complex, float8, uint16/32/64)
+        # take the pickle path like any other Python object
+        skeleton = split_tensors((args, kwargs), leaves, lambda t: t.is_cuda and str(t.dtype) in _ARENA_DTYPES) \
+            if use_arenas else (args, kwargs)
         with self._call_lock:  # the arenas carry one call at a time
             extras: Dict[int, dict] = {}
             if leaves:
@@ -175,6 +196,8 @@ class GpuSPMDSupervisor(SPMDSupervisor):
                 results.append(value)
             for dev in touched:  # one sync per GPU after ALL gathers are enqueued (they run concurrently)
                 torch.cuda.current_stream(dev).synchronize()
+            if self._retired:
+                self._free_retired(set(ranks))
         return results
 
     def _gather_result(self, r: int, skeleton, offsets):
@@ -194,6 +217,10 @@ class GpuSPMDSupervisor(SPMDSupervisor):
             arena = self.res_arenas[r].tensor(torch.uint8)
             ops.unpack(arena, offsets, outs)
         return join_tensors(skeleton, outs)
+
+
+_ARENA_DTYPES = {f"torch.{n}" for n in ("uint8", "int8", "float32", "float64", "int32", "int64", "float16", "bfloat16",
+                                           "bool", "int16")}
 
 
 def _round_up(n: int, align: int = 1 << 20) -> int:

@@ -29,6 +29,7 @@ class ProcessPool:
         self.name = name
         self._ctx = mp.get_context("spawn")  # like the reference (execution_supervisor.py:66-67)
         self._conns = []
+        self._send_locks: List[threading.Lock] = []   # one writer at a time per pipe (header+payload are two writes)
         self._procs = []
         self._pending: Dict[int, Future] = {}
         self._pending_owner: Dict[int, int] = {}
@@ -51,6 +52,7 @@ class ProcessPool:
             p.start()
             child.close()
             self._conns.append(parent)
+            self._send_locks.append(threading.Lock())
             self._procs.append(p)
         self._reader = threading.Thread(target=self._read_loop, name=f"ktb-pool-{name}", daemon=True)
         # startup handshake: each worker reports the outcome of importing the callable (id -1)
@@ -126,8 +128,10 @@ class ProcessPool:
         req = {"id": rid, "payload": payload, "method": method_name, "env": env, "serialization": serialization}
         if extra:
             req.update(extra)
+        data = pickle.dumps(req, protocol=5)
         try:
-            self._conns[idx].send_bytes(pickle.dumps(req, protocol=5))
+            with self._send_locks[idx]:   # concurrent callers (threads, async) must not interleave frames on one pipe
+                self._conns[idx].send_bytes(data)
         except (OSError, ValueError):
             self._fail_worker(idx)
         return fut
@@ -141,9 +145,10 @@ class ProcessPool:
         if self._closed:
             return
         self._closed = True
-        for c in self._conns:
+        for c, lk in zip(self._conns, self._send_locks):
             try:
-                c.send_bytes(SHUTDOWN)
+                with lk:
+                    c.send_bytes(SHUTDOWN)
             except Exception:  # noqa: BLE001
                 pass
         for p in self._procs:

@@ -116,9 +116,17 @@ class _GpuArenas:
         self.update(cfg)
 
     def update(self, cfg: dict):
+        """Open the new arena handle(s); the superseded mapping is CLOSED first (the coordinator defers the
+        cudaFree of the old arena until this rank has replied, see GpuSPMDSupervisor._grow)."""
         if cfg.get("arg_handle") is not None:
+            if self.arg_ptr:
+                self.torch.cuda.synchronize(self.device)
+                self.ops.ipc_close(self.device, self.arg_ptr)
             self.arg_ptr, self.arg_bytes = self.ops.ipc_open(self.device, cfg["arg_handle"]), int(cfg["arg_bytes"])
         if cfg.get("res_handle") is not None:
+            if self.res_ptr:
+                self.torch.cuda.synchronize(self.device)
+                self.ops.ipc_close(self.device, self.res_ptr)
             self.res_ptr, self.res_bytes = self.ops.ipc_open(self.device, cfg["res_handle"]), int(cfg["res_bytes"])
 
     def _view(self, ptr: int, dtype_name: str, shape, offset: int):
@@ -139,6 +147,17 @@ class _GpuArenas:
 
     def arg_views(self, refs, offsets):
         return [self._view(self.arg_ptr, r.dtype, r.shape, off) for r, off in zip(refs, offsets)]
+
+    def arg_tensors(self, refs, offsets):
+        """OWNED copies of the arg leaves (one ktb_unpack launch): the arena is overwritten by the next call's
+        pack + broadcast, and the reference hands every call freshly deserialised tensors — a callable may keep
+        them (`self.weights = state_dict`)."""
+        torch = self.torch
+        outs = [torch.empty(tuple(r.shape), dtype=getattr(torch, r.dtype), device=f"cuda:{self.device}") for r in refs]
+        if outs:
+            arena = self._view(self.arg_ptr, "uint8", (self.arg_bytes,), 0)
+            self.ops.unpack(arena, list(offsets), outs)
+        return outs
 
     def pack_results(self, leaves):
         """Pack result leaves into the result arena. Returns offsets, or None if the arena is too small."""
@@ -198,8 +217,8 @@ def worker_main(conn, local_rank: int, pointers, init_args, name: str, max_threa
                 collect_refs((args, kwargs), refs)
                 if refs:
                     refs.sort(key=lambda r: r.index)
-                    views = arenas.arg_views(refs, req["arg_offsets"])
-                    args, kwargs = join_tensors((args, kwargs), views)
+                    owned = arenas.arg_tensors(refs, req["arg_offsets"])
+                    args, kwargs = join_tensors((args, kwargs), owned)
             method = resolve_method(callable_obj, name, req.get("method"))
             if inspect.iscoroutinefunction(method):
                 result = asyncio.run_coroutine_threadsafe(method(*args, **kwargs), loop).result()
@@ -237,7 +256,11 @@ def worker_main(conn, local_rank: int, pointers, init_args, name: str, max_threa
             break
         if data == SHUTDOWN:
             break
-        req = pickle.loads(data)
+        try:
+            req = pickle.loads(data)
+        except Exception as e:  # noqa: BLE001 - a damaged frame is reported, it does not take the rank down
+            reply({"id": -2, "ok": False, "envelope": package_exception(e)})
+            continue
         executor.submit(run_request, req)
 
     executor.shutdown(wait=False, cancel_futures=True)

@@ -231,3 +231,39 @@ class OSInfo:
             elif req.method == "getpid":
                 out.append(OSInfoResponse(name="getpid", value=str(os.getpid())))
         return out
+
+
+# ---- stateful GPU ranks (kt.cls on rank processes; reference: tests/test_http_server.py:484-599, test_distributed.py:92-193)
+class WeightHolder:
+    """Keeps a tensor ARGUMENT across calls (the `self.weights = state_dict` pattern) and counts its calls."""
+
+    def __init__(self, scale=1):
+        self.scale = scale
+        self.kept = None
+        self.calls = 0
+
+    def keep(self, t):
+        self.calls += 1
+        self.kept = t
+        return self.calls
+
+    def kept_sum(self):
+        """[sum of the kept tensor * scale, number of keep() calls]; the kept tensor must still hold ITS bytes."""
+        self_sum = None if self.kept is None else float(self.kept.double().sum()) * self.scale
+        return [self_sum, self.calls]
+
+    def overwrite(self, t):
+        """Another tensor-carrying call between keep() and kept_sum(): must not disturb the kept tensor."""
+        return float(t.double().sum())
+
+    async def slow_echo(self, x, sleep_time=0.2):
+        import asyncio
+
+        await asyncio.sleep(sleep_time)
+        return x
+
+    def slow_sync(self, x, sleep_time=0.2):
+        import time
+
+        time.sleep(sleep_time)
+        return x

@@ -455,3 +455,30 @@ def test_fastpickle_roundtrips_and_sends_only_addressed_bytes():
     got = F.loads(F.dumps(torch.zeros(4)))
     got += 1  # results are writable tensors
     assert got.tolist() == [1.0] * 4
+
+
+def test_concurrent_large_payloads_do_not_interleave_on_the_rank_pipes():
+    """4 caller threads x 1 MiB+ tensor payloads on the same rank pipes (Connection.send_bytes writes header and
+    payload separately above 16 KiB, so unsynchronised writers corrupt the stream)."""
+    remote = kt.fn(cases.spmd_identity, name="c-concurrent").to(
+        kt.Compute(cpus="1", allowed_serialization=["json", "pickle"]).distribute("spmd", workers=1, num_proc=2))
+    try:
+        xs = [torch.full((300_000 + 1000 * i,), float(i)) for i in range(4)]
+        out = [None] * 4
+        errs = []
+
+        def work(i):
+            try:
+                for _ in range(5):
+                    out[i] = remote(xs[i], serialization="pickle")
+            except BaseException as e:  # noqa: BLE001
+                errs.append(e)
+
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+        [t.start() for t in ths]
+        [t.join(timeout=120) for t in ths]
+        assert not errs, errs
+        for i in range(4):
+            assert len(out[i]) == 2 and all(torch.equal(o, xs[i]) for o in out[i])
+    finally:
+        remote.teardown()

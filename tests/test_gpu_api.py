@@ -21,9 +21,11 @@ def _need_gpu():
     assert torch.cuda.is_available()
 
 
-def _deploy(fn, n_ranks, name):
+def _deploy(fn, n_ranks, name, placement="ranks"):
+    """placement="ranks": every call fans out into one launch per rank (ranks time-sliced on cuda:0 on a 1-GPU box:
+    same kernels, same shard arithmetic); "auto" adds the small-call lane (one launch on the root below 4 MiB)."""
     comp = kt.Compute(gpus=1, allowed_serialization=["json", "pickle"]).distribute(
-        "b200", workers=1, num_proc=n_ranks, devices=[0] * n_ranks)
+        "b200", workers=1, num_proc=n_ranks, devices=[0] * n_ranks, placement=placement)
     return kt.fn(fn, name=name).to(comp)
 
 
@@ -488,3 +490,113 @@ def test_mapped_self_check_refuses_a_wrong_declaration(monkeypatch):
     remote = kt.fn(b3_user_module.not_really_double, name="t-wrong")
     with pytest.raises(ValueError, match="self-check failed"):
         remote.to(kt.Compute(gpus=1).distribute("b200", num_proc=2, devices=[0, 0]))
+
+
+# ---- (f4) kt.cls state and concurrency on GPU rank processes ------------------------------------------------------
+def test_cls_on_gpu_ranks_keeps_owned_args_state_and_overlaps_calls():
+    """A kt.cls on GPU rank processes: (a) a CUDA tensor ARGUMENT kept across calls still holds its own bytes after
+    later calls reused the arg arena (the reference deserialises fresh tensors per call); (b) per-rank state persists
+    and a re-deploy resets it (tests/test_distributed.py:115-128); (c) async methods overlap on one loop and sync
+    methods run on the rank's thread pool (kt/serving/design.md:67-85)."""
+    import asyncio
+    import threading
+    import time
+
+    comp = kt.Compute(gpus=1, allowed_serialization=["json", "pickle"]).distribute(
+        "spmd", workers=1, num_proc=2, devices=[0, 0], arena_bytes=1 << 20)
+    holder = kt.cls(cases.WeightHolder, name="t-holder").to(comp, init_args={"scale": 2})
+    try:
+        assert holder._supervisor.__class__.__name__ == "GpuSPMDSupervisor"
+        a = torch.arange(4096, dtype=torch.float32).cuda()
+        assert holder.keep(a, serialization="pickle") == [1, 1]
+        other = torch.full((4096,), -7.0).cuda()
+        assert holder.overwrite(other, serialization="pickle") == [float(other.sum())] * 2     # reuses the arena
+        assert holder.keep(a * 3, serialization="pickle") == [2, 2]
+        got = holder.kept_sum(serialization="pickle")
+        assert got == [[float((a * 3).double().sum()) * 2, 2]] * 2, got
+        holder.keep(a, serialization="pickle")
+        holder.overwrite(other, serialization="pickle")
+        holder.overwrite(other * 2, serialization="pickle")
+        got = holder.kept_sum(serialization="pickle")
+        assert got == [[float(a.double().sum()) * 2, 3]] * 2, got         # the kept arg was NOT overwritten
+        # async methods overlap: 4 concurrent 0.25 s sleeps finish in well under 1 s
+        async def burst():
+            return await asyncio.gather(*[holder.slow_echo(i, 0.25, async_=True) for i in range(4)])
+
+        t0 = time.perf_counter()
+        res = asyncio.run(burst())
+        dt_async = time.perf_counter() - t0
+        assert res == [[i, i] for i in range(4)] and dt_async < 0.9, dt_async
+        # sync methods from caller threads run concurrently on the ranks' thread pools
+        out = [None] * 4
+
+        def work(i):
+            out[i] = holder.slow_sync(i, 0.25)
+
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+        t0 = time.perf_counter()
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+        assert out == [[i, i] for i in range(4)] and time.perf_counter() - t0 < 0.9
+        # restart_procs re-creates the rank processes: state is gone
+        assert holder.kept_sum(restart_procs=True, serialization="pickle") == [[None, 0]] * 2
+    finally:
+        holder.teardown()
+    again = kt.cls(cases.WeightHolder, name="t-holder").to(comp, init_args={"scale": 5})   # a new deploy resets state
+    try:
+        assert again.kept_sum() == [[None, 0]] * 2
+    finally:
+        again.teardown()
+
+
+def test_small_call_lane_is_indistinguishable_from_the_general_path(golden):
+    """placement="auto": calls under 4 MiB take the small-call lane (one launch on the root, no body/endpoint/header
+    work).  Same rank-ordered shards, dtypes and bits as the fan-out path and as the recorded reference results;
+    everything the lane does not cover (host tensors, kwargs, non-contiguous, empty, int tensors with a fractional
+    alpha) falls through to the general path with the general path's behaviour."""
+    double = _mapped(cases.double, "scale", alpha=2.0)
+    for world in (1, 3, 4):
+        lane = _deploy(double, world, f"t-lane-{world}", placement="auto")
+        spread = _deploy(double, world, f"t-spread-{world}", placement="ranks")
+        try:
+            assert lane._fast is not None and spread._fast is None
+            for name in ("f32_1003", "f32_3", "bf16_777", "i64_130", "i32_515"):
+                x = golden["all_inputs"][name]
+                want = ref_dispatch.spmd_call(cases.double, x, num_proc=world, serialization="pickle")
+                a = lane(x.cuda(), serialization="pickle")
+                b = spread(x.cuda(), serialization="pickle")
+                assert len(a) == len(b) == len(want) == world
+                for g, h, w in zip(a, b, want):
+                    assert g.dtype == w.dtype and tuple(g.shape) == tuple(w.shape) == tuple(h.shape), (name, world)
+                    assert torch.equal(g.cpu(), w) and torch.equal(h.cpu(), w), (name, world)
+            x2 = torch.randn(10, 37)
+            want = ref_dispatch.spmd_call(cases.double, x2, num_proc=world, serialization="pickle")
+            got = lane(x2.cuda(), serialization="pickle")
+            assert [tuple(g.shape) for g in got] == [tuple(w.shape) for w in want]
+            assert all(torch.equal(g.cpu(), w) for g, w in zip(got, want))
+            # fall-through cases behave as before
+            host = lane(x2, serialization="pickle")
+            assert all(torch.equal(g, w) for g, w in zip(host, want)) and not host[0].is_cuda
+            nc = lane(x2.cuda().t().contiguous().t(), serialization="pickle")     # non-contiguous
+            assert all(torch.equal(g.cpu(), w) for g, w in zip(nc, want))
+            assert [g.numel() for g in lane(torch.empty(0).cuda(), serialization="pickle")] == [0] * world
+            with pytest.raises(TypeError):
+                lane(x2.cuda())          # default serialization is json: tensors are not JSON (same as the general path)
+            lane.serialization = "pickle"
+            assert torch.equal(torch.cat(lane(x2.cuda())).cpu(), x2 * 2)
+        finally:
+            lane.teardown()
+            spread.teardown()
+    half = _mapped(cases.scale, "scale", alpha=0.5)     # constant fractional alpha: int tensors must not take the lane
+
+    def half_fn(x):
+        return cases._shard(x) * 0.5
+
+    half = kt.mapped("scale", alpha=0.5)(half_fn)
+    r = _deploy(half, 2, "t-lane-half", placement="auto")
+    try:
+        with pytest.raises(TypeError, match="not an integer"):
+            r(torch.arange(10).cuda(), serialization="pickle")
+        assert torch.equal(torch.cat(r(torch.arange(10.0).cuda(), serialization="pickle")).cpu(), torch.arange(10.0) * 0.5)
+    finally:
+        r.teardown()

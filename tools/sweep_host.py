@@ -1,7 +1,12 @@
 #!/usr/bin/env python
-"""Host-resident e2e experiments on N GPUs: public API with (a) an ordinary pinned tensor and (b) a pinned
-tensor whose shard pages were first-touched on each GPU's NUMA node. JSON lines → gpurun_out/sweep_host.jsonl"""
-import ctypes
+"""Host-resident e2e experiments on N GPUs.  JSON lines -> gpurun_out/sweep_host.jsonl
+
+  pcie_probe   raw copy-engine bandwidth, all selected GPUs at once: H2D only, D2H only, both — from a plain pinned
+               buffer (wherever torch put it) and from a NUMA-sharded one (ktb_host_alloc_sharded).  Shows what the
+               box can deliver whatever our pipeline does.
+  e2e_host     kt.fn(mapped).to(kt.Compute(gpus=N)) -> remote(host tensor), by input buffer kind and host mode
+  raw          ops.map_host_multi without the API layer, by chunk size and zero-copy on/off
+"""
 import json
 import os
 import sys
@@ -14,10 +19,10 @@ import torch  # noqa: E402
 
 
 def _clone(fn):
-    """A copy of an oracle callable to decorate (the shared function object stays undecorated)."""
     import types
 
     return types.FunctionType(fn.__code__, fn.__globals__, fn.__name__, fn.__defaults__, fn.__closure__)
+
 
 import kubetorch_b200 as kt  # noqa: E402
 from kubetorch_b200.device import ops  # noqa: E402
@@ -34,88 +39,122 @@ def emit(**kw):
         f.write(line + "\n")
 
 
-def gpu_numa_cpus(dev):
-    """CPUs local to GPU `dev` (sysfs), or None."""
+def numa_maps_of(ptr):
+    """N<node>=<pages> counts of the mapping that contains `ptr` (/proc/self/numa_maps), or None."""
     try:
-        bdf = torch.cuda.get_device_properties(dev).pci_bus_id if hasattr(torch.cuda.get_device_properties(dev), "pci_bus_id") else None
-    except Exception:  # noqa: BLE001
-        bdf = None
-    try:
-        import subprocess
-
-        q = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(dev)],
-                           capture_output=True, text=True).stdout.strip().lower()
-        bdf = q[4:] if q.startswith("0000") and len(q) > 12 else q
-        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
-        if node < 0:
+        best = None
+        for line in open("/proc/self/numa_maps"):
+            parts = line.split()
+            addr = int(parts[0], 16)
+            if addr <= ptr:
+                best = (addr, parts)
+        if best is None:
             return None
-        cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
-        out = set()
-        for part in cpus.split(","):
-            a, _, b = part.partition("-")
-            out.update(range(int(a), int(b or a) + 1))
-        return out
-    except Exception:  # noqa: BLE001
-        return None
+        return {p.split("=")[0]: int(p.split("=")[1]) for p in best[1] if p[0] == "N" and "=" in p}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:100]}
 
 
-def numa_pinned(n_elems, n_gpus):
-    """One contiguous fp32 tensor; shard r's pages first-touched from a thread bound to GPU r's NUMA node; then
-    page-locked in place with cudaHostRegister."""
-    x = torch.empty(n_elems, dtype=torch.float32)
-    allowed = os.sched_getaffinity(0)
+def pcie_probe(devs, n_elems, kinds):
+    nb = n_elems * 4
+    world = len(devs)
+    dev_bufs = {}
+    for d in devs:
+        b, e = ops.shard_bounds(n_elems, world, devs.index(d))
+        dev_bufs[d] = (torch.empty(e - b, device=f"cuda:{d}"), torch.empty(e - b, device=f"cuda:{d}"))
+    for kind, (xin, xout) in kinds.items():
+        for mode in ("h2d", "d2h", "both"):
+            def work(d, r, reps):
+                b, e = ops.shard_bounds(n_elems, world, r)
+                s1, s2 = torch.cuda.Stream(d), torch.cuda.Stream(d)
+                din, dout = dev_bufs[d]
+                with torch.cuda.device(d):
+                    for _ in range(reps):
+                        if mode in ("h2d", "both"):
+                            with torch.cuda.stream(s1):
+                                din.copy_(xin[b:e], non_blocking=True)
+                        if mode in ("d2h", "both"):
+                            with torch.cuda.stream(s2):
+                                xout[b:e].copy_(dout, non_blocking=True)
+                    s1.synchronize()
+                    s2.synchronize()
 
-    def touch(r):
-        cpus = gpu_numa_cpus(r)
-        if cpus:
-            try:
-                os.sched_setaffinity(0, cpus & allowed or allowed)
-            except OSError:
-                pass
-        b, e = ops.shard_bounds(n_elems, n_gpus, r)
-        x[b:e].normal_()
+            def run(reps):
+                ths = [threading.Thread(target=work, args=(d, r, reps)) for r, d in enumerate(devs)]
+                [t.start() for t in ths]
+                [t.join() for t in ths]
 
-    ths = [threading.Thread(target=touch, args=(r,)) for r in range(n_gpus)]
-    [t.start() for t in ths]
-    [t.join() for t in ths]
-    rc = torch.cuda.cudart().cudaHostRegister(x.data_ptr(), x.numel() * 4, 0)
-    assert int(rc) == 0, rc
-    return x
+            run(2)
+            t0 = time.perf_counter()
+            reps = 6
+            run(reps)
+            dt = (time.perf_counter() - t0) / reps
+            moved = nb * (2 if mode == "both" else 1)
+            emit(what="pcie_probe", devs=devs, kind=kind, mode=mode, ms=dt * 1e3, gbps_total=moved / dt / 1e9,
+                 gbps_per_gpu_per_dir=nb / world / dt / 1e9)
 
 
 def main():
     n_gpus = int(sys.argv[1]) if len(sys.argv) > 1 else torch.cuda.device_count()
+    quick = "--quick" in sys.argv
     n = 1 << 26
+    devs = list(range(n_gpus))
+    ops.ensure_init(devs)
+    emit(what="numa", nodes={d: ops.device_numa_node(d) for d in devs}, cpus=os.cpu_count(),
+         affinity=len(os.sched_getaffinity(0)))
+    plain_in = torch.randn(n).pin_memory()
+    plain_out = torch.empty(n).pin_memory()
+    t0 = time.perf_counter()
+    sh_in = ops.pinned_empty((n,), torch.float32, devices=devs)
+    t_alloc = time.perf_counter() - t0
+    sh_in.copy_(plain_in)
+    sh_out = ops.pinned_empty((n,), torch.float32, devices=devs)
+    emit(what="sharded_alloc", seconds=t_alloc, is_pinned=bool(sh_in.is_pinned()), numa_maps=numa_maps_of(sh_in.data_ptr()),
+         plain_numa_maps=numa_maps_of(plain_in.data_ptr()))
+    kinds = {"plain_pinned": (plain_in, plain_out), "numa_sharded": (sh_in, sh_out)}
+    subsets = [devs]
+    if n_gpus >= 8 and not quick:
+        subsets += [[0], [0, 1], [0, 1, 2, 3], [4, 5, 6, 7], [0, 4]]
+    for sub in subsets:
+        k2 = kinds
+        if sub != devs:   # a sharded buffer laid out for THIS subset
+            a = ops.pinned_empty((n,), torch.float32, devices=sub)
+            a.copy_(plain_in)
+            k2 = {"plain_pinned": kinds["plain_pinned"], "numa_sharded": (a, ops.pinned_empty((n,), torch.float32, devices=sub))}
+        pcie_probe(sub, n, k2)
+
     double = kt.mapped("scale", alpha=2.0)(_clone(cases.double))
-    emit(what="numa", cpus={r: (sorted(gpu_numa_cpus(r))[:2] if gpu_numa_cpus(r) else None) for r in range(n_gpus)})
-    bufs = {"plain_pinned": torch.randn(n).pin_memory(), "numa_first_touch_registered": numa_pinned(n, n_gpus)}
-    for host_mode in ("threads", "multi"):
+    for host_mode in ("multi", "threads"):
         remote = kt.fn(double, name=f"host-sweep-{host_mode}").to(
             kt.Compute(gpus=n_gpus).distribute("b200", workers=1, num_proc=n_gpus, host_mode=host_mode))
-        for kind, xh in bufs.items():
-            assert xh.is_pinned()
-            for _ in range(2):
-                out = remote(xh, serialization="pickle")
-            t0 = time.perf_counter()
-            for _ in range(8):
-                out = remote(xh, serialization="pickle")
-            dt = (time.perf_counter() - t0) / 8
-            ok = bool(torch.equal(torch.cat(out)[-4096:], xh[-4096:] * 2))
-            emit(what="e2e_host", host_mode=host_mode, kind=kind, n_gpus=n_gpus, ms=dt * 1e3,
-                 gbps=2 * n * 4 / dt / 1e9, ok=ok)
+        for kind, (xh, _) in kinds.items():
+            for zc in (0, 1):
+                if zc and host_mode != "multi":
+                    continue
+                ops.set_tuning(20, zc)
+                for _ in range(3):
+                    out = remote(xh, serialization="pickle")
+                reps = 10
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    out = remote(xh, serialization="pickle")
+                dt = (time.perf_counter() - t0) / reps
+                ok = bool(torch.equal(torch.cat(out)[-4096:], xh[-4096:] * 2)) and bool(torch.equal(out[0][:4096], xh[:4096] * 2))
+                emit(what="e2e_host", host_mode=host_mode, kind=kind, zero_copy=zc, n_gpus=n_gpus, ms=dt * 1e3,
+                     gbps=2 * n * 4 / dt / 1e9, ok=ok)
+        ops.set_tuning(20, 0)
         remote.teardown()
     # raw pipeline without the API layer, by chunk size
-    from kubetorch_b200.device import ops as _ops
-
-    xh = bufs["plain_pinned"]
-    yh = torch.empty_like(xh).pin_memory()
-    for cb in (2 << 20, 4 << 20, 8 << 20, 16 << 20):
-        _ops.map_host_multi(xh, "scale", 2.0, out_host=yh, devices=list(range(n_gpus)), chunk_bytes=cb)
-        t0 = time.perf_counter()
-        for _ in range(5):
-            _ops.map_host_multi(xh, "scale", 2.0, out_host=yh, devices=list(range(n_gpus)), chunk_bytes=cb)
-        dt = (time.perf_counter() - t0) / 5
-        emit(what="map_host_multi_raw", n_gpus=n_gpus, chunk_bytes=cb, ms=dt * 1e3, gbps=2 * n * 4 / dt / 1e9)
+    for kind, (xh, yh) in kinds.items():
+        for cb in (1 << 20, 2 << 20, 4 << 20, 8 << 20, 16 << 20):
+            for _ in range(2):
+                ops.map_host_multi(xh, "scale", 2.0, out_host=yh, devices=devs, chunk_bytes=cb)
+            t0 = time.perf_counter()
+            for _ in range(8):
+                ops.map_host_multi(xh, "scale", 2.0, out_host=yh, devices=devs, chunk_bytes=cb)
+            dt = (time.perf_counter() - t0) / 8
+            emit(what="map_host_multi_raw", kind=kind, n_gpus=n_gpus, chunk_bytes=cb, ms=dt * 1e3, gbps=2 * n * 4 / dt / 1e9,
+                 ok=bool(torch.equal(yh[-4096:], xh[-4096:] * 2)))
 
 
 if __name__ == "__main__":
