@@ -32,6 +32,20 @@ from .resources.compute import Compute  # noqa: F401
 from .resources.decorators import async_, autoscale, compute, distribute  # noqa: F401
 from .resources.inert import Image, Secret, Volume, images, secret  # noqa: F401  (call-site stand-ins, see inert.py)
 
+
+
+def pinned_empty(shape, dtype=None, gpus=None, devices=None):
+    """Uninitialised PINNED host tensor for host-resident calls.  With `gpus=N` (or explicit `devices`) the pages of
+    `x.chunk(N)[r]` are placed on the NUMA node of GPU r, so a sharded call on `kt.Compute(gpus=N)` moves every shard
+    over its own socket's memory controllers and its own GPU's PCIe link (ktb_host_alloc_sharded)."""
+    import torch
+
+    from .device import ops
+
+    devs = list(devices) if devices is not None else (list(range(int(gpus))) if gpus else None)
+    return ops.pinned_empty(shape, dtype or torch.float32, devices=devs)
+
+
 for _exc in EXCEPTION_REGISTRY.values():
     _exc.__module__ = "kubetorch_b200"
 

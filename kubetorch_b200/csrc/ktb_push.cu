@@ -5,12 +5,20 @@
 // read requests + write data one way and read data + write acks the other, and measured only ~0.6 of
 // the link per direction (profiles/r1f_sweep_peer_2gpu.jsonl).  Here both directions carry posted writes only:
 //
-//   root  : push_scatter_kernel  — for chunk c, peer-STORE chunk c of every rank's shard into that
-//           rank's staging buffer, then publish ready[r][c] = seq (st.release.sys) in the rank's memory
-//   rank r: push_consume_kernel  — spin (ld.acquire.sys, local memory) until ready[c] >= seq, apply the
-//           op to the staged chunk (local HBM read) and peer-STORE the result into the root's result
-//           arena; after the last chunk publish ack[r] = seq in the root's memory
+//   root  : push_scatter_kernel  — ONE launch per call; CTAs run chunk-major: peer-STORE chunk c of every rank's
+//           shard into that rank's staging buffer; the CTA that completes chunk c (per-chunk counter) publishes
+//           ready[r][c] = seq (st.release.sys) in every rank's memory
+//   rank r: push_consume_kernel  — ONE launch per call; the CTAs of chunk c spin (ld.acquire.sys, local memory)
+//           until ready[c] >= seq, apply the op to the staged chunk (local HBM read) and peer-STORE the result into
+//           the root's result arena; the last CTA publishes ack[r] = seq in the root's memory
 //   root  : push_wait_kernel     — stream-ordered completion: spin until every ack[r] >= seq
+//
+// Why this shape (profiles/r2_summary.md, 2-GPU duplex matrix + NVLink counters): when ONE GPU drives both
+// directions of its port (a kernel that loads from the peer and stores to it) the port delivers ~490 GB/s per
+// direction; when each side only issues posted WRITES towards the other, both directions run at 689 GB/s at the same
+// time (raw 818 GB/s per direction incl. 18.75 % write headers = 0.91 of the 900 GB/s links, acks negligible).
+// Round 1 launched one kernel per chunk on both sides: the launch boundaries drained the link 2 x 8 times per call;
+// here the chunk hand-off happens inside one resident grid per side.
 //
 // The flags replace host-side events, so the same code serves one controller process driving N GPUs
 // and one process per GPU (CUDA IPC arenas): there is no host synchronisation on the data path at all.
@@ -60,81 +68,94 @@ __device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsig
 }
 
 struct PushScatterArgs {
-  const uint8_t* src[kPushMaxRanks];             // root-local source of this chunk, per destination
-  uint8_t* dst[kPushMaxRanks];                   // peer staging destination
-  unsigned long long nbytes[kPushMaxRanks];
-  uint32_t tile_prefix[kPushMaxRanks + 1];
-  unsigned long long* ready[kPushMaxRanks];      // peer: &ready_r[chunk]
+  const uint8_t* src[kPushMaxRanks];             // root-local base of this rank's shard
+  uint8_t* dst[kPushMaxRanks];                   // peer staging base (call-parity half already applied)
+  unsigned long long shard_bytes[kPushMaxRanks];
+  unsigned long long chunk_bytes[kPushMaxRanks]; // bytes per chunk of this rank's shard (same rule as the consumer)
+  uint32_t tile_prefix[kPushMaxRanks + 1];       // tiles per chunk, prefix over ranks (identical for every chunk)
+  unsigned long long* ready[kPushMaxRanks];      // peer: ready_r[0..n_chunks)
   const unsigned long long* ack[kPushMaxRanks];  // root-local: &ack[r]
   int n;
+  int n_chunks;
   unsigned long long seq;
 };
 
 __global__ void __launch_bounds__(kPushThreads)
-    push_scatter_kernel(const __grid_constant__ PushScatterArgs a, unsigned int* ticket, unsigned int* status) {
-  const uint32_t t = blockIdx.x;
+    push_scatter_kernel(const __grid_constant__ PushScatterArgs a, unsigned int* chunk_done, unsigned int* status) {
+  const uint32_t tiles_per_chunk = a.tile_prefix[a.n];
+  const uint32_t c = blockIdx.x / tiles_per_chunk;          // chunk-major: chunk 0 of every rank goes out first
+  const uint32_t rem = blockIdx.x % tiles_per_chunk;
   int seg = 0;
-  while (seg + 1 < a.n && a.tile_prefix[seg + 1] <= t) ++seg;
+  while (seg + 1 < a.n && a.tile_prefix[seg + 1] <= rem) ++seg;
   // do not overwrite staging buffer (seq & 1) before the rank consumed call seq-2
   if (a.seq > 2) {
     if (threadIdx.x == 0) (void)spin_until(a.ack[seg], a.seq - 2, status);   // a timeout is recorded in *status
     __syncthreads();
   }
-  const size_t off = (size_t)(t - a.tile_prefix[seg]) * kPushTile;
-  const size_t seg_bytes = (size_t)a.nbytes[seg];
-  const size_t len = (seg_bytes - off) < (size_t)kPushTile ? (seg_bytes - off) : (size_t)kPushTile;
-  const uint8_t* s = a.src[seg] + off;
-  uint8_t* d = a.dst[seg] + off;
-  if (((((uintptr_t)s) | ((uintptr_t)d)) & 31) == 0) {
-    const size_t nv = len >> 5;   // a full tile = 512 packets = 2 per thread, both loads first
-    uint32_t w0[8], w1[8];
-    const size_t v0 = threadIdx.x, v1 = threadIdx.x + kPushThreads;
-    if (v0 < nv) ldg256_stream(s + (v0 << 5), w0);
-    if (v1 < nv) ldg256_stream(s + (v1 << 5), w1);
-    if (v0 < nv) stg256(d + (v0 << 5), w0);
-    if (v1 < nv) stg256(d + (v1 << 5), w1);
-    for (size_t e = (nv << 5) + threadIdx.x; e < len; e += kPushThreads) d[e] = s[e];
-  } else {
-    for (size_t e = threadIdx.x; e < len; e += kPushThreads) d[e] = s[e];
+  const size_t shard = (size_t)a.shard_bytes[seg];
+  const size_t cb = min(shard, (size_t)c * (size_t)a.chunk_bytes[seg]);
+  const size_t ce = min(shard, cb + (size_t)a.chunk_bytes[seg]);
+  const size_t off = cb + (size_t)(rem - a.tile_prefix[seg]) * kPushTile;
+  if (off < ce) {
+    const size_t len = (ce - off) < (size_t)kPushTile ? (ce - off) : (size_t)kPushTile;
+    const uint8_t* s = a.src[seg] + off;
+    uint8_t* d = a.dst[seg] + off;
+    if (((((uintptr_t)s) | ((uintptr_t)d)) & 31) == 0) {
+      const size_t nv = len >> 5;   // a full tile = 512 packets = 2 per thread, both loads first
+      uint32_t w0[8], w1[8];
+      const size_t v0 = threadIdx.x, v1 = threadIdx.x + kPushThreads;
+      if (v0 < nv) ldg256_stream(s + (v0 << 5), w0);
+      if (v1 < nv) ldg256_stream(s + (v1 << 5), w1);
+      if (v0 < nv) stg256(d + (v0 << 5), w0);
+      if (v1 < nv) stg256(d + (v1 << 5), w1);
+      for (size_t e = (nv << 5) + threadIdx.x; e < len; e += kPushThreads) d[e] = s[e];
+    } else {
+      for (size_t e = threadIdx.x; e < len; e += kPushThreads) d[e] = s[e];
+    }
   }
-  // last CTA of the launch publishes "chunk landed" to every rank
+  // the CTA that completes chunk c publishes "chunk landed" to every rank
   __shared__ bool last;
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();
-    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    last = (atomicAdd(&chunk_done[c], 1u) == tiles_per_chunk - 1);
   }
   __syncthreads();
   if (last) {
     if (threadIdx.x < a.n) {
       __threadfence_system();
-      st_release_sys(a.ready[threadIdx.x], a.seq);
+      st_release_sys(a.ready[threadIdx.x] + c, a.seq);
     }
-    if (threadIdx.x == 0) *ticket = 0;
+    if (threadIdx.x == 0) chunk_done[c] = 0;
   }
 }
 
-// Publish-only launch for empty chunks (keeps the flag protocol uniform).
+// Publish-only launch for calls with nothing to move (keeps the flag protocol uniform).
 __global__ void push_publish_kernel(const __grid_constant__ PushScatterArgs a) {
-  if (threadIdx.x < a.n) st_release_sys(a.ready[threadIdx.x], a.seq);
+  if (threadIdx.x < a.n)
+    for (int c = 0; c < a.n_chunks; ++c) st_release_sys(a.ready[threadIdx.x] + c, a.seq);
 }
 
 template <int DT, int OP>
 __global__ void __launch_bounds__(kPushThreads)
-    push_consume_kernel(const uint8_t* stage, uint8_t* dst, size_t n_bytes, MapParams p,
-                        const unsigned long long* ready, unsigned long long seq, unsigned long long* ack,
-                        int publish_ack, unsigned int* ticket, unsigned int* status) {
+    push_consume_kernel(const uint8_t* stage, uint8_t* dst, size_t shard_bytes, size_t chunk_bytes,
+                        uint32_t tiles_per_chunk, MapParams p, const unsigned long long* ready,
+                        unsigned long long seq, unsigned long long* ack, unsigned int* ticket, unsigned int* status) {
   constexpr size_t ES = (DT == KTB_U8) ? 1 : ((DT == KTB_BF16 || DT == KTB_F16) ? 2 : (DT == KTB_I64 ? 8 : 4));
+  const uint32_t c = blockIdx.x / tiles_per_chunk;      // CTAs are scheduled in order: chunk 0's tiles first
+  const uint32_t t = blockIdx.x % tiles_per_chunk;
   __shared__ bool flag;
-  if (threadIdx.x == 0) flag = spin_until(ready, seq, status);
+  if (threadIdx.x == 0) flag = spin_until(ready + c, seq, status);
   __syncthreads();
   // the piece never arrived (the wait timed out and raised the sticky status word): do NOT map stale staging data
   // into the caller's result and do NOT acknowledge — the root's wait then times out too and the host maps the
   // status to PodTerminatedError; the session is torn down, so the unbalanced ticket does not matter
   if (!flag) return;
-  const size_t off = (size_t)blockIdx.x * kPushTile;
-  if (off < n_bytes) {
-    const size_t len = (n_bytes - off) < (size_t)kPushTile ? (n_bytes - off) : (size_t)kPushTile;
+  const size_t cb = min(shard_bytes, (size_t)c * chunk_bytes);
+  const size_t ce = min(shard_bytes, cb + chunk_bytes);
+  const size_t off = cb + (size_t)t * kPushTile;
+  if (off < ce) {
+    const size_t len = (ce - off) < (size_t)kPushTile ? (ce - off) : (size_t)kPushTile;
     const uint8_t* s = stage + off;
     uint8_t* d = dst + off;
     if (((((uintptr_t)s) | ((uintptr_t)d)) & 31) == 0) {
@@ -158,19 +179,17 @@ __global__ void __launch_bounds__(kPushThreads)
       for (size_t e = threadIdx.x; e < len / ES; e += kPushThreads) apply_elem<DT, OP>(s + e * ES, d + e * ES, p);
     }
   }
-  if (publish_ack) {
-    __shared__ bool last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence_system();
-      last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (last && threadIdx.x == 0) {
-      __threadfence_system();
-      st_release_sys(ack, seq);   // results of the whole shard are in the root's memory
-      *ticket = 0;
-    }
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence_system();
+    st_release_sys(ack, seq);   // results of the whole shard are in the root's memory
+    *ticket = 0;
   }
 }
 
@@ -203,10 +222,12 @@ size_t ktb_push_control_bytes(void) { return 4096; }
 //   [ 512, 1024)  ack[r]    (u64 per rank, written by rank r into the ROOT's block)
 //   [1024, 1028)  ticket    (u32, local)
 //   [1032, 1036)  status    (u32, local; nonzero = a spin timed out)
+//   [2048, 2304)  chunk_done[c]  (u32 per chunk, root-local: finished tiles of chunk c in the running call)
 #define KTB_CTRL_READY 0
 #define KTB_CTRL_ACK 512
 #define KTB_CTRL_TICKET 1024
 #define KTB_CTRL_STATUS 1032
+#define KTB_CTRL_CHUNK_DONE 2048
 #define KTB_PUSH_MAX_CHUNKS 64
 
 int ktb_push_scatter(int root_dev, const void* src_root, size_t n_elems, size_t granule, int dtype, int n_ranks,
@@ -225,39 +246,41 @@ int ktb_push_scatter(int root_dev, const void* src_root, size_t n_elems, size_t 
   KTB_GUARD(root_dev);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* croot = static_cast<uint8_t*>(ctrl_root);
-  unsigned int* ticket = reinterpret_cast<unsigned int*>(croot + KTB_CTRL_TICKET);
+  unsigned int* chunk_done = reinterpret_cast<unsigned int*>(croot + KTB_CTRL_CHUNK_DONE);
   unsigned int* status = reinterpret_cast<unsigned int*>(croot + KTB_CTRL_STATUS);
   const size_t buf_off = (size_t)(seq & 1) * stage_stride;
-  for (int c = 0; c < n_chunks; ++c) {
-    PushScatterArgs a;
-    a.n = 0;
-    a.seq = seq;
-    a.tile_prefix[0] = 0;
-    for (int r = 0; r < n_ranks; ++r) {
-      if (r == root_rank) continue;
-      size_t sb = 0, se = 0, cb = 0, ce = 0;
-      ktb_shard_bounds(n_elems / granule, n_ranks, r, &sb, &se);
-      sb *= granule;
-      se *= granule;
-      chunk_bounds(se - sb, n_chunks, c, &cb, &ce);
-      KTB_REQUIRE(stage_peer[r] && ctrl_peer[r], KTB_ERR_ARG, "ktb_push_scatter: rank %d has no staging/control block", r);
-      KTB_REQUIRE((se - sb) * es <= stage_stride, KTB_ERR_ARG, "ktb_push_scatter: shard of rank %d exceeds stage_stride", r);
-      const int i = a.n++;
-      a.src[i] = static_cast<const uint8_t*>(src_root) + (sb + cb) * es;
-      a.dst[i] = static_cast<uint8_t*>(stage_peer[r]) + buf_off + cb * es;
-      a.nbytes[i] = (ce - cb) * es;
-      a.tile_prefix[i + 1] = a.tile_prefix[i] + (uint32_t)(((ce - cb) * es + kPushTile - 1) / kPushTile);
-      a.ready[i] = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ctrl_peer[r]) + KTB_CTRL_READY) + c;
-      a.ack[i] = reinterpret_cast<const unsigned long long*>(croot + KTB_CTRL_ACK) + r;
-    }
-    if (a.n == 0) continue;
-    const uint32_t tiles = a.tile_prefix[a.n];
-    if (tiles == 0)
-      push_publish_kernel<<<1, 32, 0, st>>>(a);
-    else
-      push_scatter_kernel<<<tiles, kPushThreads, 0, st>>>(a, ticket, status);
-    KTB_CK(cudaGetLastError());
+  PushScatterArgs a;
+  a.n = 0;
+  a.n_chunks = n_chunks;
+  a.seq = seq;
+  a.tile_prefix[0] = 0;
+  for (int r = 0; r < n_ranks; ++r) {
+    if (r == root_rank) continue;
+    size_t sb = 0, se = 0, c0b = 0, c0e = 0, per = 0, dummy = 0;
+    ktb_shard_bounds(n_elems / granule, n_ranks, r, &sb, &se);
+    sb *= granule;
+    se *= granule;
+    chunk_bounds(se - sb, n_chunks, 0, &c0b, &c0e);
+    chunk_bounds(se - sb, n_chunks, 1, &per, &dummy);   // start of chunk 1 = elements per chunk
+    if (per == 0) per = c0e - c0b;                      // single-chunk (or empty) shard
+    KTB_REQUIRE(stage_peer[r] && ctrl_peer[r], KTB_ERR_ARG, "ktb_push_scatter: rank %d has no staging/control block", r);
+    KTB_REQUIRE((se - sb) * es <= stage_stride, KTB_ERR_ARG, "ktb_push_scatter: shard of rank %d exceeds stage_stride", r);
+    const int i = a.n++;
+    a.src[i] = static_cast<const uint8_t*>(src_root) + sb * es;
+    a.dst[i] = static_cast<uint8_t*>(stage_peer[r]) + buf_off;
+    a.shard_bytes[i] = (se - sb) * es;
+    a.chunk_bytes[i] = per * es;
+    a.tile_prefix[i + 1] = a.tile_prefix[i] + (uint32_t)((per * es + kPushTile - 1) / kPushTile);
+    a.ready[i] = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ctrl_peer[r]) + KTB_CTRL_READY);
+    a.ack[i] = reinterpret_cast<const unsigned long long*>(croot + KTB_CTRL_ACK) + r;
   }
+  if (a.n == 0) return KTB_OK;
+  const uint32_t tiles_per_chunk = a.tile_prefix[a.n];
+  if (tiles_per_chunk == 0)
+    push_publish_kernel<<<1, 32, 0, st>>>(a);
+  else
+    push_scatter_kernel<<<tiles_per_chunk * (uint32_t)n_chunks, kPushThreads, 0, st>>>(a, chunk_done, status);
+  KTB_CK(cudaGetLastError());
   return KTB_OK;
 }
 
@@ -284,30 +307,30 @@ int ktb_push_consume(int dev, int op, int dtype, const void* stage_local, size_t
   unsigned long long* ack =
       reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ctrl_root_peer) + KTB_CTRL_ACK) + rank;
   const uint8_t* stage = static_cast<const uint8_t*>(stage_local) + (size_t)(seq & 1) * stage_stride;
-  for (int c = 0; c < n_chunks; ++c) {
-    size_t cb = 0, ce = 0;
-    chunk_bounds(shard_elems, n_chunks, c, &cb, &ce);
-    const size_t nb = (ce - cb) * es;
-    const unsigned grid = (unsigned)std::max<size_t>(1, (nb + kPushTile - 1) / kPushTile);
-    const int publish = (c == n_chunks - 1) ? 1 : 0;
-    const uint8_t* s = stage + cb * es;
-    uint8_t* d = static_cast<uint8_t*>(dst_root_shard) + cb * es;
+  size_t per = 0, dummy = 0, c0b = 0, c0e = 0;
+  chunk_bounds(shard_elems, n_chunks, 0, &c0b, &c0e);
+  chunk_bounds(shard_elems, n_chunks, 1, &per, &dummy);
+  if (per == 0) per = c0e - c0b;
+  const size_t chunk_bytes = per * es, shard_bytes = shard_elems * es;
+  const uint32_t tpc = (uint32_t)std::max<size_t>(1, (chunk_bytes + kPushTile - 1) / kPushTile);
+  const unsigned grid = tpc * (unsigned)n_chunks;
+  uint8_t* d = static_cast<uint8_t*>(dst_root_shard);
 #define KTB_PC(DT, OPC)                                                                                       \
-  push_consume_kernel<DT, OPC><<<grid, kPushThreads, 0, st>>>(s, d, nb, p, ready + c, seq, ack, publish, ticket, status)
-    if (op == KTB_OP_IDENTITY) {
-      KTB_PC(KTB_U8, KTB_OP_IDENTITY);
-    } else {
-      switch (dtype) {
-        case KTB_F32: if (op == KTB_OP_SCALE) KTB_PC(KTB_F32, KTB_OP_SCALE); else KTB_PC(KTB_F32, KTB_OP_AFFINE); break;
-        case KTB_BF16: if (op == KTB_OP_SCALE) KTB_PC(KTB_BF16, KTB_OP_SCALE); else KTB_PC(KTB_BF16, KTB_OP_AFFINE); break;
-        case KTB_I32: if (op == KTB_OP_SCALE) KTB_PC(KTB_I32, KTB_OP_SCALE); else KTB_PC(KTB_I32, KTB_OP_AFFINE); break;
-        case KTB_F16: if (op == KTB_OP_SCALE) KTB_PC(KTB_F16, KTB_OP_SCALE); else KTB_PC(KTB_F16, KTB_OP_AFFINE); break;
-        default: if (op == KTB_OP_SCALE) KTB_PC(KTB_I64, KTB_OP_SCALE); else KTB_PC(KTB_I64, KTB_OP_AFFINE); break;
-      }
+  push_consume_kernel<DT, OPC><<<grid, kPushThreads, 0, st>>>(stage, d, shard_bytes, chunk_bytes, tpc, p, ready, seq, \
+                                                              ack, ticket, status)
+  if (op == KTB_OP_IDENTITY) {
+    KTB_PC(KTB_U8, KTB_OP_IDENTITY);
+  } else {
+    switch (dtype) {
+      case KTB_F32: if (op == KTB_OP_SCALE) KTB_PC(KTB_F32, KTB_OP_SCALE); else KTB_PC(KTB_F32, KTB_OP_AFFINE); break;
+      case KTB_BF16: if (op == KTB_OP_SCALE) KTB_PC(KTB_BF16, KTB_OP_SCALE); else KTB_PC(KTB_BF16, KTB_OP_AFFINE); break;
+      case KTB_I32: if (op == KTB_OP_SCALE) KTB_PC(KTB_I32, KTB_OP_SCALE); else KTB_PC(KTB_I32, KTB_OP_AFFINE); break;
+      case KTB_F16: if (op == KTB_OP_SCALE) KTB_PC(KTB_F16, KTB_OP_SCALE); else KTB_PC(KTB_F16, KTB_OP_AFFINE); break;
+      default: if (op == KTB_OP_SCALE) KTB_PC(KTB_I64, KTB_OP_SCALE); else KTB_PC(KTB_I64, KTB_OP_AFFINE); break;
     }
-#undef KTB_PC
-    KTB_CK(cudaGetLastError());
   }
+#undef KTB_PC
+  KTB_CK(cudaGetLastError());
   return KTB_OK;
 }
 

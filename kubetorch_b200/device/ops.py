@@ -511,7 +511,7 @@ class PushSession:
     kernel waits in-kernel for its piece, maps it and pushes the result into the root's result
     buffer. No events between devices: flags in device memory order everything."""
 
-    def __init__(self, devices: Sequence[int], max_shard_bytes: int, n_chunks: int = 8):
+    def __init__(self, devices: Sequence[int], max_shard_bytes: int, n_chunks: int = 16):
         self.devices = [int(d) for d in devices]
         ensure_init(set(self.devices))
         self.root = self.devices[0]
@@ -527,6 +527,8 @@ class PushSession:
         n = len(self.devices)
         # host mirror of every control block's sticky status word, refreshed by an async D2H copy behind each call:
         # a timed-out in-kernel wait is seen at the NEXT call without a host sync on the data path
+        self._side = torch.cuda.Stream(self.root)       # the root's own shard maps beside the scatter, not behind it
+        self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
         self._status_host = torch.zeros(n, dtype=torch.int32).pin_memory()
         self._status_dev = [c[1032:1036].view(torch.int32) for c in self.ctrl]
         self._stage_ptrs = L.arr(ctypes.c_void_p, [0 if s is None else s.data_ptr() for s in self.stage])
@@ -543,6 +545,18 @@ class PushSession:
         rows = x_root.numel() // gran
         dt = dtype_code(x_root.dtype)
         root_stream = _stream(self.root, None)
+        b, e = shard_bounds(rows, n, 0)  # the root's own shard, on the root's HBM, on a side stream forked BEFORE the scatter
+        # launch (an event recorded after it would order the side stream behind the whole scatter)
+        own = e > b
+        if own:
+            with torch.cuda.device(self.root):
+                cur = torch.cuda.current_stream(self.root)
+                self._ev_fork.record(cur)
+                self._side.wait_event(self._ev_fork)
+                L.call("ktb_map", self.root, OPS[op], dt, x_root.data_ptr() + b * gran * es,
+                       out_root.data_ptr() + b * gran * es, (e - b) * gran, float(alpha), float(beta), L.VARIANT_AUTO,
+                       int(self._side.cuda_stream))
+                self._ev_join.record(self._side)
         L.call("ktb_push_scatter", self.root, x_root.data_ptr(), x_root.numel(), gran, dt, n, 0, self._stage_ptrs,
                self.stride, self._ctrl_ptrs, self.ctrl[0].data_ptr(), self.n_chunks, seq, root_stream)
         for r in range(1, n):
@@ -553,12 +567,10 @@ class PushSession:
                    out_root.data_ptr() + b * gran * es, (e - b) * gran, float(alpha), float(beta),
                    self.ctrl[r].data_ptr(), self.ctrl[0].data_ptr(), r, self.n_chunks, seq,
                    _stream(self.devices[r], None))
-        b, e = shard_bounds(rows, n, 0)  # the root's own shard, on the root's HBM
-        if e > b:
-            L.call("ktb_map", self.root, OPS[op], dt, x_root.data_ptr() + b * gran * es,
-                   out_root.data_ptr() + b * gran * es, (e - b) * gran, float(alpha), float(beta), L.VARIANT_AUTO,
-                   root_stream)
         L.call("ktb_push_wait", self.root, self.ctrl[0].data_ptr(), n, 0, seq, root_stream)
+        if own:
+            with torch.cuda.device(self.root):
+                torch.cuda.current_stream(self.root).wait_event(self._ev_join)
         for r, d in enumerate(self.devices):   # stream-ordered behind this call's kernels on each device
             with torch.cuda.device(d):
                 self._status_host[r:r + 1].copy_(self._status_dev[r], non_blocking=True)

@@ -149,7 +149,14 @@ class GpuSPMDSupervisor(SPMDSupervisor):
         # take the pickle path like any other Python object
         skeleton = split_tensors((args, kwargs), leaves, lambda t: t.is_cuda and str(t.dtype) in _ARENA_DTYPES) \
             if use_arenas else (args, kwargs)
-        with self._call_lock:  # the arenas carry one call at a time
+        # The arenas carry one call at a time, so a call that moves CUDA tensors through them is serialised.  Calls
+        # WITHOUT tensor args run concurrently (the reference's concurrency model: thread callers and async callables
+        # overlap, kt/serving/design.md:67-85); their CUDA results, if any, travel pickled instead of through the
+        # result arena.
+        import contextlib
+
+        locked = bool(leaves)
+        with (self._call_lock if locked else contextlib.nullcontext()):
             extras: Dict[int, dict] = {}
             if leaves:
                 from ..device import ops
@@ -172,10 +179,10 @@ class GpuSPMDSupervisor(SPMDSupervisor):
                         ops.broadcast(root_arena[:total], dsts)                   # one read, N-1 peer stores
                     torch.cuda.current_stream(root).synchronize()                 # data is in every rank's HBM
                 for r in ranks:
-                    extras[r] = {"arg_offsets": offsets}
-            for r in ranks:
-                if r in self._pending_updates:
-                    extras.setdefault(r, {})["arena_update"] = self._pending_updates.pop(r)
+                    extras[r] = {"arg_offsets": offsets, "res_arena": True}
+                for r in ranks:
+                    if r in self._pending_updates:
+                        extras.setdefault(r, {})["arena_update"] = self._pending_updates.pop(r)
             payload = fastpickle.dumps(skeleton)   # CPU tensor leaves as raw bytes; CUDA leaves were moved to the arena
             envs = self.rank_envs()
             futures = self.pool.call_all(payload, method_name, envs, serialization, ranks=ranks, extras=extras)
@@ -196,7 +203,7 @@ class GpuSPMDSupervisor(SPMDSupervisor):
                 results.append(value)
             for dev in touched:  # one sync per GPU after ALL gathers are enqueued (they run concurrently)
                 torch.cuda.current_stream(dev).synchronize()
-            if self._retired:
+            if locked and self._retired:
                 self._free_retired(set(ranks))
         return results
 

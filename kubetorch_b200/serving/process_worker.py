@@ -229,7 +229,7 @@ def worker_main(conn, local_rank: int, pointers, init_args, name: str, max_threa
                         return await x
                     result = asyncio.run_coroutine_threadsafe(_await(result), loop).result()
             extra = {}
-            if arenas is not None and req["serialization"] != "json":
+            if arenas is not None and req.get("res_arena") and req["serialization"] != "json":
                 from .tensor_wire import split_tensors
 
                 leaves = []
