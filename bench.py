@@ -389,14 +389,15 @@ def run_ours(args):
             bb, ee = ops.shard_bounds(n // gran, world, rank)
             if rank == 0:
                 cur = torch.cuda.current_stream(dev)
-                if ee > bb:   # the root's own shard maps on a side stream, beside the scatter
+                if ee > bb:   # fork point BEFORE the scatter launch; the own-shard map is launched after it (side stream)
                     ev_fork.record(cur)
+                L.call("ktb_push_scatter", dev, x_ptr + off, n, gran, dt, world, 0, c_stage, stride, c_ctrl,
+                       ctrl_root_ptr, n_chunks, seq, stream)
+                if ee > bb:
                     side.wait_event(ev_fork)
                     L.call("ktb_map", dev, op, dt, x_ptr + off + bb * gran * e_, y_ptr + off + bb * gran * e_,
                            (ee - bb) * gran, float(a), float(b), L.VARIANT_AUTO, side.cuda_stream)
                     ev_join.record(side)
-                L.call("ktb_push_scatter", dev, x_ptr + off, n, gran, dt, world, 0, c_stage, stride, c_ctrl,
-                       ctrl_root_ptr, n_chunks, seq, stream)
                 L.call("ktb_push_wait", dev, ctrl_root_ptr, world, 0, seq, stream)
                 if ee > bb:
                     cur.wait_event(ev_join)

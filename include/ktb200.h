@@ -209,6 +209,13 @@ int ktb_push_scatter(int root_dev, const void* src_root, size_t n_elems, size_t 
                      int n_ranks, int root_rank, void* const* stage_peer, size_t stage_stride,
                      void* const* ctrl_peer, void* ctrl_root, int n_chunks, unsigned long long seq,
                      uintptr_t stream);
+/* The same root side with pieces of EXACTLY chunk_elems elements per rank (n_chunks = ceil(largest shard /
+ * chunk_elems) <= 64): for consumers that need whole work units per piece (ktb_mlp_bf16_pushed: GEMM row chunks).
+ * ctas_per_sm caps the persistent grid (0 = library default) so the root's own compute keeps its share of every SM. */
+int ktb_push_scatter_chunked(int root_dev, const void* src_root, size_t n_elems, size_t granule, int dtype,
+                             int n_ranks, int root_rank, void* const* stage_peer, size_t stage_stride,
+                             void* const* ctrl_peer, void* ctrl_root, size_t chunk_elems, int ctas_per_sm,
+                             unsigned long long seq, uintptr_t stream);
 /* RANK side: for each piece, spin in-kernel until ready[chunk] >= seq, then
  * dst_root_shard[piece] = op(stage_local[piece]) (peer stores into the root's result arena); after the
  * last piece publish ack[rank] = seq in the root's control block (ctrl_root_peer). */
@@ -260,6 +267,17 @@ size_t ktb_mlp_stage_bytes(size_t M, int d_in);
 int ktb_mlp_bf16_staged(int dev, const void* obs_peer, size_t M, int d_in, int d_hidden, int d_out,
                         const void* W1, const void* W2, const void* W3, void* logits, void* scratch,
                         void* stage, uintptr_t stream);
+
+/* Push-fed form for a rank whose observation rows are PUSHED by the root (ktb_push_scatter_chunked with
+ * chunk_elems = chunk_rows * d_in into stage_local, double-buffered by call parity with stride stage_stride):
+ * before each row chunk's GEMMs a one-warp kernel waits in-stream for ready[chunk] >= seq; the logits are stored
+ * straight into `logits` (a peer pointer into the root's result: fused gather) and ack[rank] = seq is published in
+ * the root's control block behind the last chunk.  Root NVLink egress carries posted writes only (689 GB/s measured
+ * with the result stream flowing the other way, against 403 GB/s when seven ranks pull). */
+int ktb_mlp_bf16_pushed(int dev, const void* stage_local, size_t stage_stride, size_t M, int d_in, int d_hidden,
+                        int d_out, const void* W1, const void* W2, const void* W3, void* logits, void* scratch,
+                        void* ctrl_local, void* ctrl_root_peer, int rank, size_t chunk_rows, unsigned long long seq,
+                        uintptr_t stream);
 
 #ifdef __cplusplus
 }

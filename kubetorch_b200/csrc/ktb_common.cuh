@@ -323,7 +323,52 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_all() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
+// ---- in-kernel flag synchronisation of the push pipeline (ktb_push.cu, ktb_mlp.cu) ------------------------------
+constexpr unsigned long long kSpinTimeoutNs = 10ull * 1000 * 1000 * 1000;  // 10 s
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Spin until *flag >= want. Returns false on timeout (and records it in *status).
+__device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long want,
+                                           unsigned int* status) {
+  if (ld_acquire_sys(flag) >= want) return true;
+  const unsigned long long t0 = globaltimer_ns();
+  while (ld_acquire_sys(flag) < want) {
+    __nanosleep(200);
+    if (globaltimer_ns() - t0 > kSpinTimeoutNs) {
+      atomicExch(status, 1u);
+      return false;
+    }
+  }
+  return true;
+}
+
 #endif  // __CUDACC__
+
+// Layout of a control block (zero-initialised, one per device, ktb_push_control_bytes() long):
+//   [   0,  512)  ready[c]  (u64 per chunk, written by the root into the RANK's block)
+//   [ 512, 1024)  ack[r]    (u64 per rank, written by rank r into the ROOT's block)
+//   [1024, 1028)  ticket    (u32, local)
+//   [1032, 1036)  status    (u32, local; nonzero = a spin timed out)
+//   [2048, 2304)  chunk_done[c]  (u32 per chunk, root-local: finished tiles of chunk c in the running call)
+#define KTB_CTRL_READY 0
+#define KTB_CTRL_ACK 512
+#define KTB_CTRL_TICKET 1024
+#define KTB_CTRL_STATUS 1032
+#define KTB_CTRL_CHUNK_DONE 2048
+#define KTB_PUSH_MAX_CHUNKS 64
+
 
 // ---- kernel-launch entry points shared between translation units --------------------------------
 // (ktb_map.cu) enqueue dst = op(src) on the current device.

@@ -1526,6 +1526,77 @@ static int mlp_run(int dev, const void* obs, size_t M, int d_in, int d_hidden, i
   return KTB_OK;
 }
 
+// ---- pushed form: the root PUSHES this rank's observation rows chunk by chunk (ktb_push_scatter_chunked) ------------
+namespace ktb {
+// Stream-ordered "chunk c has landed": one warp spins on the local ready flag (a timeout raises the sticky status).
+__global__ void mlp_wait_ready_kernel(const unsigned long long* ready, unsigned long long seq, unsigned int* status) {
+  if (threadIdx.x == 0) (void)spin_until(ready, seq, status);
+}
+// Stream-ordered completion of the rank's call: everything before it on the stream (incl. the peer-stored logits)
+// is visible system-wide before the root sees ack[rank] = seq.
+__global__ void mlp_ack_kernel(unsigned long long* ack, unsigned long long seq) {
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    st_release_sys(ack, seq);
+  }
+}
+}  // namespace ktb
+
+int ktb_mlp_bf16_pushed(int dev, const void* stage_local, size_t stage_stride, size_t M, int d_in, int d_hidden, int d_out,
+                        const void* W1, const void* W2, const void* W3, void* logits, void* scratch, void* ctrl_local,
+                        void* ctrl_root_peer, int rank, size_t chunk_rows, unsigned long long seq, uintptr_t stream) {
+  int rc = require_device(dev);
+  if (rc) return rc;
+  KTB_REQUIRE(stage_local && ctrl_local && ctrl_root_peer && W1 && W2 && W3 && scratch && (logits || M == 0), KTB_ERR_ARG,
+              "ktb_mlp_bf16_pushed: null argument");
+  KTB_REQUIRE(rank >= 0 && rank < 16 && seq > 0, KTB_ERR_ARG, "ktb_mlp_bf16_pushed: bad rank/seq");
+  KTB_REQUIRE(M % kMlpBlockM == 0, KTB_ERR_ARG, "ktb_mlp_bf16_pushed: M=%zu must be a multiple of %d", M, kMlpBlockM);
+  KTB_REQUIRE(chunk_rows > 0 && chunk_rows % kMlpBlockM == 0, KTB_ERR_ARG,
+              "ktb_mlp_bf16_pushed: chunk_rows=%zu must be a positive multiple of %d", chunk_rows, kMlpBlockM);
+  KTB_REQUIRE(d_in > 0 && d_in % kMlpBlockK == 0 && d_hidden > 0 && d_hidden % 256 == 0, KTB_ERR_ARG,
+              "ktb_mlp_bf16_pushed: d_in %% 64 and d_hidden %% 256 must be 0");
+  KTB_REQUIRE(d_out == 64, KTB_ERR_UNSUPPORTED, "ktb_mlp_bf16_pushed: d_out=%d (this build carries the 64-wide head)", d_out);
+  const size_t n_chunks = (M + chunk_rows - 1) / chunk_rows;
+  KTB_REQUIRE(n_chunks <= KTB_PUSH_MAX_CHUNKS, KTB_ERR_ARG, "ktb_mlp_bf16_pushed: %zu chunks exceed %d", n_chunks,
+              KTB_PUSH_MAX_CHUNKS);
+  KTB_REQUIRE(M * (size_t)d_in * 2 <= stage_stride, KTB_ERR_ARG, "ktb_mlp_bf16_pushed: shard exceeds stage_stride");
+  rc = get_encoder();
+  if (rc) return rc;
+  KTB_GUARD(dev);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* cl = static_cast<uint8_t*>(ctrl_local);
+  const unsigned long long* ready = reinterpret_cast<const unsigned long long*>(cl + KTB_CTRL_READY);
+  unsigned int* status = reinterpret_cast<unsigned int*>(cl + KTB_CTRL_STATUS);
+  unsigned long long* ack =
+      reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ctrl_root_peer) + KTB_CTRL_ACK) + rank;
+  const __nv_bfloat16* x =
+      reinterpret_cast<const __nv_bfloat16*>(static_cast<const uint8_t*>(stage_local) + (size_t)(seq & 1) * stage_stride);
+  __nv_bfloat16* h1 = static_cast<__nv_bfloat16*>(scratch);
+  __nv_bfloat16* h2 = h1 + std::min(chunk_rows, M) * (size_t)d_hidden;
+  __nv_bfloat16* y = static_cast<__nv_bfloat16*>(logits);
+  size_t c = 0;
+  for (size_t r0 = 0; r0 < M; r0 += chunk_rows, ++c) {
+    const size_t rows = std::min(chunk_rows, M - r0);
+    mlp_wait_ready_kernel<<<1, 32, 0, st>>>(ready + c, seq, status);
+    KTB_CK(cudaGetLastError());
+    const __nv_bfloat16* a1 = x + r0 * d_in;
+    rc = launch_gemm<256, 4, true>(dev, a1, W1, h1, rows, d_hidden, d_in, d_hidden, st);
+    if (rc) return rc;
+    if (g_mlp_fuse_head && g_mlp_persistent && g_mlp_2sm && rows % 256 == 0) {
+      rc = launch_l2_head_fused(dev, h1, W2, W3, y + r0 * d_out, rows, d_hidden, d_out, st);
+      if (rc) return rc;
+      continue;
+    }
+    rc = launch_gemm<256, 4, true>(dev, h1, W2, h2, rows, d_hidden, d_hidden, d_hidden, st);
+    if (rc) return rc;
+    rc = launch_gemm<64, 4, false>(dev, h2, W3, y + r0 * d_out, rows, d_out, d_hidden, d_out, st);
+    if (rc) return rc;
+  }
+  mlp_ack_kernel<<<1, 32, 0, st>>>(ack, seq);
+  KTB_CK(cudaGetLastError());
+  return KTB_OK;
+}
+
 int ktb_mlp_bf16(int dev, const void* obs, size_t M, int d_in, int d_hidden, int d_out, const void* W1,
                  const void* W2, const void* W3, void* logits, void* scratch, uintptr_t stream) {
   return mlp_run(dev, obs, M, d_in, d_hidden, d_out, W1, W2, W3, logits, scratch, nullptr, stream);

@@ -31,42 +31,13 @@
 #include "ktb_common.cuh"
 
 #include <algorithm>
+#include <atomic>
 
 namespace ktb {
 
 constexpr int kPushMaxRanks = 16;
 constexpr int kPushThreads = 256;
 constexpr uint32_t kPushTile = 16384;          // bytes per CTA
-constexpr unsigned long long kSpinTimeoutNs = 10ull * 1000 * 1000 * 1000;  // 10 s
-
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// Spin until *flag >= want. Returns false on timeout (and records it in *status).
-__device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long want,
-                                           unsigned int* status) {
-  if (ld_acquire_sys(flag) >= want) return true;
-  const unsigned long long t0 = globaltimer_ns();
-  while (ld_acquire_sys(flag) < want) {
-    __nanosleep(200);
-    if (globaltimer_ns() - t0 > kSpinTimeoutNs) {
-      atomicExch(status, 1u);
-      return false;
-    }
-  }
-  return true;
-}
-
 struct PushScatterArgs {
   const uint8_t* src[kPushMaxRanks];             // root-local base of this rank's shard
   uint8_t* dst[kPushMaxRanks];                   // peer staging base (call-parity half already applied)
@@ -83,51 +54,68 @@ struct PushScatterArgs {
 __global__ void __launch_bounds__(kPushThreads)
     push_scatter_kernel(const __grid_constant__ PushScatterArgs a, unsigned int* chunk_done, unsigned int* status) {
   const uint32_t tiles_per_chunk = a.tile_prefix[a.n];
-  const uint32_t c = blockIdx.x / tiles_per_chunk;          // chunk-major: chunk 0 of every rank goes out first
-  const uint32_t rem = blockIdx.x % tiles_per_chunk;
-  int seg = 0;
-  while (seg + 1 < a.n && a.tile_prefix[seg + 1] <= rem) ++seg;
-  // do not overwrite staging buffer (seq & 1) before the rank consumed call seq-2
-  if (a.seq > 2) {
-    if (threadIdx.x == 0) (void)spin_until(a.ack[seg], a.seq - 2, status);   // a timeout is recorded in *status
-    __syncthreads();
-  }
-  const size_t shard = (size_t)a.shard_bytes[seg];
-  const size_t cb = min(shard, (size_t)c * (size_t)a.chunk_bytes[seg]);
-  const size_t ce = min(shard, cb + (size_t)a.chunk_bytes[seg]);
-  const size_t off = cb + (size_t)(rem - a.tile_prefix[seg]) * kPushTile;
-  if (off < ce) {
-    const size_t len = (ce - off) < (size_t)kPushTile ? (ce - off) : (size_t)kPushTile;
-    const uint8_t* s = a.src[seg] + off;
-    uint8_t* d = a.dst[seg] + off;
-    if (((((uintptr_t)s) | ((uintptr_t)d)) & 31) == 0) {
-      const size_t nv = len >> 5;   // a full tile = 512 packets = 2 per thread, both loads first
-      uint32_t w0[8], w1[8];
-      const size_t v0 = threadIdx.x, v1 = threadIdx.x + kPushThreads;
-      if (v0 < nv) ldg256_stream(s + (v0 << 5), w0);
-      if (v1 < nv) ldg256_stream(s + (v1 << 5), w1);
-      if (v0 < nv) stg256(d + (v0 << 5), w0);
-      if (v1 < nv) stg256(d + (v1 << 5), w1);
-      for (size_t e = (nv << 5) + threadIdx.x; e < len; e += kPushThreads) d[e] = s[e];
-    } else {
-      for (size_t e = threadIdx.x; e < len; e += kPushThreads) d[e] = s[e];
-    }
-  }
-  // the CTA that completes chunk c publishes "chunk landed" to every rank
+  const uint32_t total_tiles = tiles_per_chunk * (uint32_t)a.n_chunks;
   __shared__ bool last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    last = (atomicAdd(&chunk_done[c], 1u) == tiles_per_chunk - 1);
-  }
-  __syncthreads();
-  if (last) {
-    if (threadIdx.x < a.n) {
+  // Persistent grid (the launch caps the CTAs per SM so that other kernels of the root — its own shard's map, the
+  // MLP of rank 0 — keep their share of every SM).  Every CTA walks the tiles in increasing order = chunk-major and
+  // reports its finished tiles ONCE per chunk (one system fence + one atomic per CTA per chunk, not per tile: the
+  // fence has to wait for the acknowledgement of every peer store the CTA has in flight).
+  uint32_t cur_chunk = 0xffffffffu, n_done = 0;
+  auto flush = [&]() {   // all threads call it together
+    __syncthreads();     // every thread's stores of the finished tiles are issued
+    if (threadIdx.x == 0) {
       __threadfence_system();
-      st_release_sys(a.ready[threadIdx.x] + c, a.seq);
+      last = (atomicAdd(&chunk_done[cur_chunk], n_done) + n_done == tiles_per_chunk);
     }
-    if (threadIdx.x == 0) chunk_done[c] = 0;
+    __syncthreads();
+    if (last) {          // this CTA completed the chunk: publish "chunk landed" to every rank
+      if (threadIdx.x < a.n) {
+        __threadfence_system();
+        st_release_sys(a.ready[threadIdx.x] + cur_chunk, a.seq);
+      }
+      if (threadIdx.x == 0) chunk_done[cur_chunk] = 0;
+    }
+    __syncthreads();     // `last` is reused
+  };
+  for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const uint32_t c = tile / tiles_per_chunk;                // chunk 0 of every rank goes out first
+    const uint32_t rem = tile % tiles_per_chunk;
+    if (c != cur_chunk) {
+      if (n_done) flush();
+      cur_chunk = c;
+      n_done = 0;
+    }
+    int seg = 0;
+    while (seg + 1 < a.n && a.tile_prefix[seg + 1] <= rem) ++seg;
+    // do not overwrite staging buffer (seq & 1) before the rank consumed call seq-2
+    if (a.seq > 2) {
+      if (threadIdx.x == 0) (void)spin_until(a.ack[seg], a.seq - 2, status);   // a timeout is recorded in *status
+      __syncthreads();
+    }
+    const size_t shard = (size_t)a.shard_bytes[seg];
+    const size_t cb = min(shard, (size_t)c * (size_t)a.chunk_bytes[seg]);
+    const size_t ce = min(shard, cb + (size_t)a.chunk_bytes[seg]);
+    const size_t off = cb + (size_t)(rem - a.tile_prefix[seg]) * kPushTile;
+    if (off < ce) {
+      const size_t len = (ce - off) < (size_t)kPushTile ? (ce - off) : (size_t)kPushTile;
+      const uint8_t* s = a.src[seg] + off;
+      uint8_t* d = a.dst[seg] + off;
+      if (((((uintptr_t)s) | ((uintptr_t)d)) & 31) == 0) {
+        const size_t nv = len >> 5;   // a full tile = 512 packets = 2 per thread, both loads first
+        uint32_t w0[8], w1[8];
+        const size_t v0 = threadIdx.x, v1 = threadIdx.x + kPushThreads;
+        if (v0 < nv) ldg256_stream(s + (v0 << 5), w0);
+        if (v1 < nv) ldg256_stream(s + (v1 << 5), w1);
+        if (v0 < nv) stg256(d + (v0 << 5), w0);
+        if (v1 < nv) stg256(d + (v1 << 5), w1);
+        for (size_t e = (nv << 5) + threadIdx.x; e < len; e += kPushThreads) d[e] = s[e];
+      } else {
+        for (size_t e = threadIdx.x; e < len; e += kPushThreads) d[e] = s[e];
+      }
+    }
+    ++n_done;
   }
+  if (n_done) flush();
 }
 
 // Publish-only launch for calls with nothing to move (keeps the flag protocol uniform).
@@ -139,44 +127,54 @@ __global__ void push_publish_kernel(const __grid_constant__ PushScatterArgs a) {
 template <int DT, int OP>
 __global__ void __launch_bounds__(kPushThreads)
     push_consume_kernel(const uint8_t* stage, uint8_t* dst, size_t shard_bytes, size_t chunk_bytes,
-                        uint32_t tiles_per_chunk, MapParams p, const unsigned long long* ready,
+                        uint32_t tiles_per_chunk, uint32_t n_chunks, MapParams p, const unsigned long long* ready,
                         unsigned long long seq, unsigned long long* ack, unsigned int* ticket, unsigned int* status) {
   constexpr size_t ES = (DT == KTB_U8) ? 1 : ((DT == KTB_BF16 || DT == KTB_F16) ? 2 : (DT == KTB_I64 ? 8 : 4));
-  const uint32_t c = blockIdx.x / tiles_per_chunk;      // CTAs are scheduled in order: chunk 0's tiles first
-  const uint32_t t = blockIdx.x % tiles_per_chunk;
+  const uint32_t total_tiles = tiles_per_chunk * n_chunks;
   __shared__ bool flag;
-  if (threadIdx.x == 0) flag = spin_until(ready + c, seq, status);
-  __syncthreads();
-  // the piece never arrived (the wait timed out and raised the sticky status word): do NOT map stale staging data
-  // into the caller's result and do NOT acknowledge — the root's wait then times out too and the host maps the
-  // status to PodTerminatedError; the session is torn down, so the unbalanced ticket does not matter
-  if (!flag) return;
-  const size_t cb = min(shard_bytes, (size_t)c * chunk_bytes);
-  const size_t ce = min(shard_bytes, cb + chunk_bytes);
-  const size_t off = cb + (size_t)t * kPushTile;
-  if (off < ce) {
-    const size_t len = (ce - off) < (size_t)kPushTile ? (ce - off) : (size_t)kPushTile;
-    const uint8_t* s = stage + off;
-    uint8_t* d = dst + off;
-    if (((((uintptr_t)s) | ((uintptr_t)d)) & 31) == 0) {
-      const size_t nv = len >> 5;
-      uint32_t w0[8], w1[8];
-      const size_t v0 = threadIdx.x, v1 = threadIdx.x + kPushThreads;
-      if (v0 < nv) ldg256_stream(s + (v0 << 5), w0);
-      if (v1 < nv) ldg256_stream(s + (v1 << 5), w1);
-      if (v0 < nv) {
-        apply_words<DT, OP, 8>(w0, p);
-        stg256(d + (v0 << 5), w0);
+  uint32_t have = 0;   // chunks [0, have) are known to have landed
+  // persistent grid, tiles in increasing order = chunk order; ONE system fence per CTA (before the ack ticket), not per
+  // tile: the fence waits for the acknowledgement of every peer store the CTA has in flight
+  for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const uint32_t c = tile / tiles_per_chunk;
+    const uint32_t t = tile % tiles_per_chunk;
+    if (c >= have) {
+      if (threadIdx.x == 0) flag = spin_until(ready + c, seq, status);
+      __syncthreads();
+      // the piece never arrived (the wait timed out and raised the sticky status word): do NOT map stale staging
+      // data into the caller's result and do NOT acknowledge — the root's wait then times out too and the host maps
+      // the status to PodTerminatedError; the session is torn down, so the unbalanced ticket does not matter
+      if (!flag) return;
+      have = c + 1;
+      __syncthreads();   // `flag` is reused
+    }
+    const size_t cb = min(shard_bytes, (size_t)c * chunk_bytes);
+    const size_t ce = min(shard_bytes, cb + chunk_bytes);
+    const size_t off = cb + (size_t)t * kPushTile;
+    if (off < ce) {
+      const size_t len = (ce - off) < (size_t)kPushTile ? (ce - off) : (size_t)kPushTile;
+      const uint8_t* s = stage + off;
+      uint8_t* d = dst + off;
+      if (((((uintptr_t)s) | ((uintptr_t)d)) & 31) == 0) {
+        const size_t nv = len >> 5;
+        uint32_t w0[8], w1[8];
+        const size_t v0 = threadIdx.x, v1 = threadIdx.x + kPushThreads;
+        if (v0 < nv) ldg256_stream(s + (v0 << 5), w0);
+        if (v1 < nv) ldg256_stream(s + (v1 << 5), w1);
+        if (v0 < nv) {
+          apply_words<DT, OP, 8>(w0, p);
+          stg256(d + (v0 << 5), w0);
+        }
+        if (v1 < nv) {
+          apply_words<DT, OP, 8>(w1, p);
+          stg256(d + (v1 << 5), w1);
+        }
+        const size_t tail = nv << 5;
+        for (size_t e = threadIdx.x; e < (len - tail) / ES; e += kPushThreads)
+          apply_elem<DT, OP>(s + tail + e * ES, d + tail + e * ES, p);
+      } else {
+        for (size_t e = threadIdx.x; e < len / ES; e += kPushThreads) apply_elem<DT, OP>(s + e * ES, d + e * ES, p);
       }
-      if (v1 < nv) {
-        apply_words<DT, OP, 8>(w1, p);
-        stg256(d + (v1 << 5), w1);
-      }
-      const size_t tail = nv << 5;
-      for (size_t e = threadIdx.x; e < (len - tail) / ES; e += kPushThreads)
-        apply_elem<DT, OP>(s + tail + e * ES, d + tail + e * ES, p);
-    } else {
-      for (size_t e = threadIdx.x; e < len / ES; e += kPushThreads) apply_elem<DT, OP>(s + e * ES, d + e * ES, p);
     }
   }
   __shared__ bool last;
@@ -217,32 +215,30 @@ extern "C" {
 
 size_t ktb_push_control_bytes(void) { return 4096; }
 
-// Layout of a control block (zero-initialised, one per device, ktb_push_control_bytes() long):
-//   [   0,  512)  ready[c]  (u64 per chunk, written by the root into the RANK's block)
-//   [ 512, 1024)  ack[r]    (u64 per rank, written by rank r into the ROOT's block)
-//   [1024, 1028)  ticket    (u32, local)
-//   [1032, 1036)  status    (u32, local; nonzero = a spin timed out)
-//   [2048, 2304)  chunk_done[c]  (u32 per chunk, root-local: finished tiles of chunk c in the running call)
-#define KTB_CTRL_READY 0
-#define KTB_CTRL_ACK 512
-#define KTB_CTRL_TICKET 1024
-#define KTB_CTRL_STATUS 1032
-#define KTB_CTRL_CHUNK_DONE 2048
-#define KTB_PUSH_MAX_CHUNKS 64
+// (control-block layout: KTB_CTRL_* in ktb_common.cuh)
 
-int ktb_push_scatter(int root_dev, const void* src_root, size_t n_elems, size_t granule, int dtype, int n_ranks,
-                     int root_rank, void* const* stage_peer, size_t stage_stride, void* const* ctrl_peer,
-                     void* ctrl_root, int n_chunks, unsigned long long seq, uintptr_t stream) {
+std::atomic<int> g_push_scatter_ctas_per_sm{8};   // ktb_set_tuning(21, n)
+
+// chunk_elems == 0: n_chunks pieces per shard (chunk_bounds); otherwise pieces of exactly chunk_elems elements
+// (the consumer of ktb_mlp_bf16_pushed wants whole GEMM row chunks), n_chunks = ceil(largest shard / chunk_elems).
+static int push_scatter_impl(const char* who, int root_dev, const void* src_root, size_t n_elems, size_t granule, int dtype,
+                             int n_ranks, int root_rank, void* const* stage_peer, size_t stage_stride,
+                             void* const* ctrl_peer, void* ctrl_root, int n_chunks, size_t chunk_elems,
+                             unsigned long long seq, int ctas_per_sm, uintptr_t stream) {
   int rc = require_device(root_dev);
   if (rc) return rc;
   const size_t es = dtype_size(dtype);
-  KTB_REQUIRE(es != 0, KTB_ERR_ARG, "ktb_push_scatter: unknown dtype %d", dtype);
+  KTB_REQUIRE(es != 0, KTB_ERR_ARG, "%s: unknown dtype %d", who, dtype);
   KTB_REQUIRE(n_ranks > 0 && n_ranks <= kPushMaxRanks && root_rank >= 0 && root_rank < n_ranks, KTB_ERR_ARG,
-              "ktb_push_scatter: bad ranks %d/%d", root_rank, n_ranks);
-  KTB_REQUIRE(n_chunks > 0 && n_chunks <= KTB_PUSH_MAX_CHUNKS, KTB_ERR_ARG, "ktb_push_scatter: n_chunks %d out of range",
-              n_chunks);
-  KTB_REQUIRE(src_root && stage_peer && ctrl_peer && ctrl_root && seq > 0, KTB_ERR_ARG, "ktb_push_scatter: null argument");
-  KTB_REQUIRE(granule > 0 && n_elems % granule == 0, KTB_ERR_ARG, "ktb_push_scatter: n_elems not a multiple of granule");
+              "%s: bad ranks %d/%d", who, root_rank, n_ranks);
+  KTB_REQUIRE(src_root && stage_peer && ctrl_peer && ctrl_root && seq > 0, KTB_ERR_ARG, "%s: null argument", who);
+  KTB_REQUIRE(granule > 0 && n_elems % granule == 0, KTB_ERR_ARG, "%s: n_elems not a multiple of granule", who);
+  if (chunk_elems) {
+    size_t b0 = 0, e0 = 0;
+    ktb_shard_bounds(n_elems / granule, n_ranks, 0, &b0, &e0);   // rank 0 holds the largest shard
+    n_chunks = (int)std::max<size_t>(1, ((e0 - b0) * granule + chunk_elems - 1) / chunk_elems);
+  }
+  KTB_REQUIRE(n_chunks > 0 && n_chunks <= KTB_PUSH_MAX_CHUNKS, KTB_ERR_ARG, "%s: n_chunks %d out of range", who, n_chunks);
   KTB_GUARD(root_dev);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* croot = static_cast<uint8_t*>(ctrl_root);
@@ -256,15 +252,17 @@ int ktb_push_scatter(int root_dev, const void* src_root, size_t n_elems, size_t 
   a.tile_prefix[0] = 0;
   for (int r = 0; r < n_ranks; ++r) {
     if (r == root_rank) continue;
-    size_t sb = 0, se = 0, c0b = 0, c0e = 0, per = 0, dummy = 0;
+    size_t sb = 0, se = 0, c0b = 0, c0e = 0, per = chunk_elems, dummy = 0;
     ktb_shard_bounds(n_elems / granule, n_ranks, r, &sb, &se);
     sb *= granule;
     se *= granule;
-    chunk_bounds(se - sb, n_chunks, 0, &c0b, &c0e);
-    chunk_bounds(se - sb, n_chunks, 1, &per, &dummy);   // start of chunk 1 = elements per chunk
-    if (per == 0) per = c0e - c0b;                      // single-chunk (or empty) shard
-    KTB_REQUIRE(stage_peer[r] && ctrl_peer[r], KTB_ERR_ARG, "ktb_push_scatter: rank %d has no staging/control block", r);
-    KTB_REQUIRE((se - sb) * es <= stage_stride, KTB_ERR_ARG, "ktb_push_scatter: shard of rank %d exceeds stage_stride", r);
+    if (!chunk_elems) {
+      chunk_bounds(se - sb, n_chunks, 0, &c0b, &c0e);
+      chunk_bounds(se - sb, n_chunks, 1, &per, &dummy);   // start of chunk 1 = elements per chunk
+      if (per == 0) per = c0e - c0b;                      // single-chunk (or empty) shard
+    }
+    KTB_REQUIRE(stage_peer[r] && ctrl_peer[r], KTB_ERR_ARG, "%s: rank %d has no staging/control block", who, r);
+    KTB_REQUIRE((se - sb) * es <= stage_stride, KTB_ERR_ARG, "%s: shard of rank %d exceeds stage_stride", who, r);
     const int i = a.n++;
     a.src[i] = static_cast<const uint8_t*>(src_root) + sb * es;
     a.dst[i] = static_cast<uint8_t*>(stage_peer[r]) + buf_off;
@@ -276,12 +274,32 @@ int ktb_push_scatter(int root_dev, const void* src_root, size_t n_elems, size_t 
   }
   if (a.n == 0) return KTB_OK;
   const uint32_t tiles_per_chunk = a.tile_prefix[a.n];
-  if (tiles_per_chunk == 0)
+  if (tiles_per_chunk == 0) {
     push_publish_kernel<<<1, 32, 0, st>>>(a);
-  else
-    push_scatter_kernel<<<tiles_per_chunk * (uint32_t)n_chunks, kPushThreads, 0, st>>>(a, chunk_done, status);
+  } else {
+    const size_t total = (size_t)tiles_per_chunk * (size_t)n_chunks;
+    if (ctas_per_sm <= 0) ctas_per_sm = g_push_scatter_ctas_per_sm.load();
+    const size_t cap = (size_t)device_info(root_dev)->sm_count * (size_t)std::max(1, ctas_per_sm);
+    push_scatter_kernel<<<(unsigned)std::min(total, cap), kPushThreads, 0, st>>>(a, chunk_done, status);
+  }
   KTB_CK(cudaGetLastError());
   return KTB_OK;
+}
+
+int ktb_push_scatter(int root_dev, const void* src_root, size_t n_elems, size_t granule, int dtype, int n_ranks,
+                     int root_rank, void* const* stage_peer, size_t stage_stride, void* const* ctrl_peer,
+                     void* ctrl_root, int n_chunks, unsigned long long seq, uintptr_t stream) {
+  return push_scatter_impl("ktb_push_scatter", root_dev, src_root, n_elems, granule, dtype, n_ranks, root_rank, stage_peer,
+                           stage_stride, ctrl_peer, ctrl_root, n_chunks, 0, seq, 0, stream);
+}
+
+int ktb_push_scatter_chunked(int root_dev, const void* src_root, size_t n_elems, size_t granule, int dtype, int n_ranks,
+                             int root_rank, void* const* stage_peer, size_t stage_stride, void* const* ctrl_peer,
+                             void* ctrl_root, size_t chunk_elems, int ctas_per_sm, unsigned long long seq,
+                             uintptr_t stream) {
+  KTB_REQUIRE(chunk_elems > 0, KTB_ERR_ARG, "ktb_push_scatter_chunked: chunk_elems must be positive");
+  return push_scatter_impl("ktb_push_scatter_chunked", root_dev, src_root, n_elems, granule, dtype, n_ranks, root_rank,
+                           stage_peer, stage_stride, ctrl_peer, ctrl_root, 0, chunk_elems, seq, ctas_per_sm, stream);
 }
 
 int ktb_push_consume(int dev, int op, int dtype, const void* stage_local, size_t stage_stride, void* dst_root_shard,
@@ -313,11 +331,12 @@ int ktb_push_consume(int dev, int op, int dtype, const void* stage_local, size_t
   if (per == 0) per = c0e - c0b;
   const size_t chunk_bytes = per * es, shard_bytes = shard_elems * es;
   const uint32_t tpc = (uint32_t)std::max<size_t>(1, (chunk_bytes + kPushTile - 1) / kPushTile);
-  const unsigned grid = tpc * (unsigned)n_chunks;
+  const size_t total = (size_t)tpc * (size_t)n_chunks;
+  const unsigned grid = (unsigned)std::min(total, (size_t)device_info(dev)->sm_count * 8);
   uint8_t* d = static_cast<uint8_t*>(dst_root_shard);
 #define KTB_PC(DT, OPC)                                                                                       \
-  push_consume_kernel<DT, OPC><<<grid, kPushThreads, 0, st>>>(stage, d, shard_bytes, chunk_bytes, tpc, p, ready, seq, \
-                                                              ack, ticket, status)
+  push_consume_kernel<DT, OPC><<<grid, kPushThreads, 0, st>>>(stage, d, shard_bytes, chunk_bytes, tpc, (uint32_t)n_chunks, p, \
+                                                              ready, seq, ack, ticket, status)
   if (op == KTB_OP_IDENTITY) {
     KTB_PC(KTB_U8, KTB_OP_IDENTITY);
   } else {

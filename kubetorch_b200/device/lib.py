@@ -73,6 +73,9 @@ _SIGNATURES = {
     "ktb_push_control_bytes": (c_size_t, []),
     "ktb_push_scatter": (c_int, [c_int, c_void_p, c_size_t, c_size_t, c_int, c_int, c_int, POINTER(c_void_p), c_size_t,
                                  POINTER(c_void_p), c_void_p, c_int, ctypes.c_ulonglong, c_uintptr]),
+    "ktb_push_scatter_chunked": (c_int, [c_int, c_void_p, c_size_t, c_size_t, c_int, c_int, c_int, POINTER(c_void_p),
+                                         c_size_t, POINTER(c_void_p), c_void_p, c_size_t, c_int, ctypes.c_ulonglong,
+                                         c_uintptr]),
     "ktb_push_consume": (c_int, [c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_double, c_double,
                                  c_void_p, c_void_p, c_int, c_int, ctypes.c_ulonglong, c_uintptr]),
     "ktb_push_wait": (c_int, [c_int, c_void_p, c_int, c_int, ctypes.c_ulonglong, c_uintptr]),
@@ -85,6 +88,9 @@ _SIGNATURES = {
     "ktb_mlp_stage_bytes": (c_size_t, [c_size_t, c_int]),
     "ktb_mlp_bf16_staged": (c_int, [c_int, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_uintptr]),
+    "ktb_mlp_bf16_pushed": (c_int, [c_int, c_void_p, c_size_t, c_size_t, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_size_t, ctypes.c_ulonglong,
+                                    c_uintptr]),
     # experiment knob, not in the stable header
     "ktb_set_tuning": (c_int, [c_int, c_int]),
 }

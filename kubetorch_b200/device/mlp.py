@@ -84,8 +84,89 @@ def _weights_on(dev: int, ws: Sequence[torch.Tensor]) -> List[torch.Tensor]:
     return out
 
 
+PUSH_CHUNK_ROWS = 37888      # two waves of 74 CTA pairs x 256 rows: whole waves for the fused layer-2+head kernel
+_push_states = {}
+
+
+class _MlpPushState:
+    """Per device set: control blocks, per-rank staging (2 call-parity halves), the root's side stream."""
+
+    def __init__(self, devs: Sequence[int], stride: int):
+        self.devs, self.stride, self.seq = list(devs), int(stride), 0
+        cb = L.load().ktb_push_control_bytes()
+        self.ctrl = [torch.zeros(cb, dtype=torch.uint8, device=f"cuda:{d}") for d in devs]
+        self.stage = [None if r == 0 else torch.empty(2 * self.stride, dtype=torch.uint8, device=f"cuda:{d}")
+                      for r, d in enumerate(devs)]
+        for d in set(devs):
+            torch.cuda.synchronize(d)
+        self.stage_ptrs = L.arr(ctypes.c_void_p, [0 if t is None else t.data_ptr() for t in self.stage])
+        self.ctrl_ptrs = L.arr(ctypes.c_void_p, [c.data_ptr() for c in self.ctrl])
+        self.side = torch.cuda.Stream(devs[0])
+        self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
+        self.status_host = torch.zeros(len(devs), dtype=torch.int32).pin_memory()
+        self.status_dev = [c[1032:1036].view(torch.int32) for c in self.ctrl]
+
+
+def _mlp_push_state(devs: Sequence[int], shard_bytes: int) -> _MlpPushState:
+    key = tuple(devs)
+    st = _push_states.get(key)
+    stride = (int(shard_bytes) + 255) // 256 * 256
+    if st is None or st.stride < stride:
+        st = _push_states[key] = _MlpPushState(devs, stride)
+    return st
+
+
+def _mlp_scatter_gather_pushed(obs_root, w1, w2, w3, devs, out_root, bounds, weights) -> None:
+    """The root PUSHES each rank's observation rows in GEMM-sized chunks (posted NVLink writes, flags in device memory);
+    every rank's GEMM chain consumes chunk c as soon as it has landed and stores its logits straight into the root's
+    result; the root's own shard runs on a side stream beside the scatter.  No host synchronisation, no events between
+    devices."""
+    root, n = devs[0], len(devs)
+    d_in, d_hidden, d_out = obs_root.shape[1], w1.shape[0], w3.shape[0]
+    st = _mlp_push_state(devs, max(e - b for b, e in bounds) * d_in * 2)
+    if bool(st.status_host.any()):
+        _push_states.pop(tuple(devs), None)
+        raise ops.PushTimeout("MLP push pipeline: an in-kernel wait timed out during an earlier call")
+    st.seq += 1
+    seq = st.seq
+    root_stream = torch.cuda.current_stream(root)
+    with torch.cuda.device(root):
+        b0, e0 = bounds[0]
+        st.ev_fork.record(root_stream)          # forked BEFORE the scatter launch: the side stream must not queue behind it
+        st.side.wait_event(st.ev_fork)
+        if e0 > b0:
+            ws = weights[root]
+            mlp_forward(obs_root[b0:e0], ws[0], ws[1], ws[2], out=out_root[b0:e0], device=root, stream=st.side, staged=False)
+        st.ev_join.record(st.side)
+        L.call("ktb_push_scatter_chunked", root, obs_root.data_ptr(), obs_root.numel(), d_in, L.BF16, n, 0, st.stage_ptrs,
+               st.stride, st.ctrl_ptrs, st.ctrl[0].data_ptr(), PUSH_CHUNK_ROWS * d_in, 1, seq, int(root_stream.cuda_stream))
+    streams = {d: torch.cuda.current_stream(d) for d in devs[1:]}
+    scratch = {d: _scratch_for(d, max(e - b for b, e in bounds), d_hidden) for d in devs[1:]}
+
+    def issue(r):
+        dev = devs[r]
+        b, e = bounds[r]
+        ws = weights[dev]
+        L.call("ktb_mlp_bf16_pushed", dev, st.stage[r].data_ptr(), st.stride, e - b, d_in, d_hidden, d_out, ws[0].data_ptr(),
+               ws[1].data_ptr(), ws[2].data_ptr(), out_root[b:e].data_ptr() if e > b else 0, scratch[dev].data_ptr(),
+               st.ctrl[r].data_ptr(), st.ctrl[0].data_ptr(), r, PUSH_CHUNK_ROWS, seq, int(streams[dev].cuda_stream))
+
+    global _pool
+    if _pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _pool = ThreadPoolExecutor(max_workers=16, thread_name_prefix="ktb-mlp")
+    list(_pool.map(issue, range(1, n)))
+    with torch.cuda.device(root):
+        L.call("ktb_push_wait", root, st.ctrl[0].data_ptr(), n, 0, seq, int(root_stream.cuda_stream))
+        root_stream.wait_event(st.ev_join)
+    for r, d in enumerate(devs):   # stream-ordered mirror of the sticky status words (seen at the next call)
+        with torch.cuda.device(d):
+            st.status_host[r:r + 1].copy_(st.status_dev[r], non_blocking=True)
+
+
 def mlp_scatter_gather(obs_root: torch.Tensor, w1, w2, w3, devices: Sequence[int],
-                       out_root: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+                       out_root: Optional[torch.Tensor] = None, transfer: str = "auto") -> List[torch.Tensor]:
     """Rank r runs the MLP on `obs.chunk(world)[r]`: its first GEMM's TMA loads read the rows straight
     from the root GPU (scatter) and its last epilogue stores the logits straight into the root's
     result buffer (gather). Returns rank-ordered views of the root result."""
@@ -104,6 +185,16 @@ def mlp_scatter_gather(obs_root: torch.Tensor, w1, w2, w3, devices: Sequence[int
     bounds = [ops.shard_bounds(M, len(devs), r) for r in range(len(devs))]
     views = [out_root[b:e] for b, e in bounds]
     weights = {dev: _weights_on(dev, (w1, w2, w3)) for dev in set(devs)}
+    distinct = len(set(devs)) == len(devs) and len(devs) > 1
+    pushable = distinct and all((e - b) % 128 == 0 for b, e in bounds) and \
+        -(-max(e - b for b, e in bounds) // PUSH_CHUNK_ROWS) <= 64
+    if transfer not in ("auto", "pull", "push"):
+        raise ValueError("transfer must be 'auto', 'pull' or 'push'")
+    if transfer == "push" and not pushable:
+        raise ValueError("push transfer needs distinct devices and shards of a multiple of 128 rows")
+    if pushable and transfer != "pull":
+        _mlp_scatter_gather_pushed(obs_root, w1, w2, w3, devs, out_root, bounds, weights)
+        return views
     for dev in set(devs):       # allocate scratch/staging on the calling thread (allocator + first use)
         _scratch_for(dev, max(e - b for b, e in bounds), w1.shape[0])
         if dev != root:

@@ -545,20 +545,22 @@ class PushSession:
         rows = x_root.numel() // gran
         dt = dtype_code(x_root.dtype)
         root_stream = _stream(self.root, None)
-        b, e = shard_bounds(rows, n, 0)  # the root's own shard, on the root's HBM, on a side stream forked BEFORE the scatter
-        # launch (an event recorded after it would order the side stream behind the whole scatter)
+        b, e = shard_bounds(rows, n, 0)  # the root's own shard maps on the root's HBM, on a side stream
         own = e > b
-        if own:
+        if own:   # the fork point is recorded BEFORE the scatter launch (an event recorded after it would order the side
+            # stream behind the whole scatter) ...
             with torch.cuda.device(self.root):
-                cur = torch.cuda.current_stream(self.root)
-                self._ev_fork.record(cur)
+                self._ev_fork.record(torch.cuda.current_stream(self.root))
+        L.call("ktb_push_scatter", self.root, x_root.data_ptr(), x_root.numel(), gran, dt, n, 0, self._stage_ptrs,
+               self.stride, self._ctrl_ptrs, self.ctrl[0].data_ptr(), self.n_chunks, seq, root_stream)
+        if own:   # ... but the map kernel is LAUNCHED after the scatter: the scatter's persistent CTAs (a few per SM) take
+            # their slots first and the HBM-bound map fills the rest, instead of the scatter queueing behind 8192 map CTAs
+            with torch.cuda.device(self.root):
                 self._side.wait_event(self._ev_fork)
                 L.call("ktb_map", self.root, OPS[op], dt, x_root.data_ptr() + b * gran * es,
                        out_root.data_ptr() + b * gran * es, (e - b) * gran, float(alpha), float(beta), L.VARIANT_AUTO,
                        int(self._side.cuda_stream))
                 self._ev_join.record(self._side)
-        L.call("ktb_push_scatter", self.root, x_root.data_ptr(), x_root.numel(), gran, dt, n, 0, self._stage_ptrs,
-               self.stride, self._ctrl_ptrs, self.ctrl[0].data_ptr(), self.n_chunks, seq, root_stream)
         for r in range(1, n):
             b, e = shard_bounds(rows, n, r)
             if (e - b) * gran * es > self.stride:

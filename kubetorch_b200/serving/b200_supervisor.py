@@ -257,7 +257,7 @@ class B200Supervisor:
             return None
         integral = float(spec.alpha).is_integer() and float(spec.beta).is_integer()
         world, root, distributed = self.world_size, self.devices[0], self.distributed
-        if self.placement == "ranks" and world > 1 and len(set(self.devices)) == world:
+        if self.placement == "ranks" and world > 1:
             return None                      # explicit spread placement: every call fans out, whatever its size
         spread_ok = self.placement == "auto" and world > 1 and len(set(self.devices)) == world
         small = self.SMALL_CALL_BYTES
@@ -502,5 +502,8 @@ class B200Supervisor:
 
         names = list(bound)
         obs, w1, w2, w3 = (bound[n] for n in names[:4])
-        out = mlp.mlp_scatter_gather(obs, w1, w2, w3, devices=self.devices)
+        try:
+            out = mlp.mlp_scatter_gather(obs, w1, w2, w3, devices=self.devices, transfer=self.transfer)
+        except self.ops.PushTimeout as e:
+            self._raise_device_timeout(e)
         return out if self._all_ranks(ranks) else [out[r] for r in ranks]
