@@ -216,6 +216,14 @@ int ktb_push_scatter_chunked(int root_dev, const void* src_root, size_t n_elems,
                              int n_ranks, int root_rank, void* const* stage_peer, size_t stage_stride,
                              void* const* ctrl_peer, void* ctrl_root, size_t chunk_elems, int ctas_per_sm,
                              unsigned long long seq, uintptr_t stream);
+/* Copy-engine form of the chunked root side: every piece is a cudaMemcpyPeerAsync on a per-destination library
+ * stream of the root followed by a one-thread flag publish, issued chunk-major; NO SM of the root moves data, so its
+ * own compute (rank 0's GEMMs in ktb_mlp_bf16_pushed deployments) keeps the whole GPU.  `stream` is ordered before
+ * (sources ready) and after (sources reusable) the copies.  devs[r] = device of rank r. */
+int ktb_push_scatter_ce(int root_dev, const void* src_root, size_t n_elems, size_t granule, int dtype, int n_ranks,
+                        int root_rank, const int* devs, void* const* stage_peer, size_t stage_stride,
+                        void* const* ctrl_peer, void* ctrl_root, size_t chunk_elems, unsigned long long seq,
+                        uintptr_t stream);
 /* RANK side: for each piece, spin in-kernel until ready[chunk] >= seq, then
  * dst_root_shard[piece] = op(stage_local[piece]) (peer stores into the root's result arena); after the
  * last piece publish ack[rank] = seq in the root's control block (ctrl_root_peer). */

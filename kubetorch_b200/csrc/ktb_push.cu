@@ -32,6 +32,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 
 namespace ktb {
 
@@ -217,7 +218,10 @@ size_t ktb_push_control_bytes(void) { return 4096; }
 
 // (control-block layout: KTB_CTRL_* in ktb_common.cuh)
 
-std::atomic<int> g_push_scatter_ctas_per_sm{8};   // ktb_set_tuning(21, n)
+// 0 = one tile per CTA (measured best, profiles/r2_summary.md §2: the root's NVLink egress needs ALL thread slots
+// of the GPU in flight — 8 persistent CTAs per SM reach 380 GB/s per direction, 4: 355, 1-2: 260-290, against 430+
+// for short-lived CTAs that let the side stream's kernels interleave); n > 0 caps a persistent grid at n CTAs per SM
+std::atomic<int> g_push_scatter_ctas_per_sm{0};   // ktb_set_tuning(21, n)
 
 // chunk_elems == 0: n_chunks pieces per shard (chunk_bounds); otherwise pieces of exactly chunk_elems elements
 // (the consumer of ktb_mlp_bf16_pushed wants whole GEMM row chunks), n_chunks = ceil(largest shard / chunk_elems).
@@ -279,7 +283,7 @@ static int push_scatter_impl(const char* who, int root_dev, const void* src_root
   } else {
     const size_t total = (size_t)tiles_per_chunk * (size_t)n_chunks;
     if (ctas_per_sm <= 0) ctas_per_sm = g_push_scatter_ctas_per_sm.load();
-    const size_t cap = (size_t)device_info(root_dev)->sm_count * (size_t)std::max(1, ctas_per_sm);
+    const size_t cap = ctas_per_sm > 0 ? (size_t)device_info(root_dev)->sm_count * (size_t)ctas_per_sm : total;
     push_scatter_kernel<<<(unsigned)std::min(total, cap), kPushThreads, 0, st>>>(a, chunk_done, status);
   }
   KTB_CK(cudaGetLastError());
@@ -300,6 +304,93 @@ int ktb_push_scatter_chunked(int root_dev, const void* src_root, size_t n_elems,
   KTB_REQUIRE(chunk_elems > 0, KTB_ERR_ARG, "ktb_push_scatter_chunked: chunk_elems must be positive");
   return push_scatter_impl("ktb_push_scatter_chunked", root_dev, src_root, n_elems, granule, dtype, n_ranks, root_rank,
                            stage_peer, stage_stride, ctrl_peer, ctrl_root, 0, chunk_elems, seq, ctas_per_sm, stream);
+}
+
+// ---- copy-engine form of the root side: no SM of the root is used ------------------------------------------------
+namespace ktb {
+__global__ void push_publish_one_kernel(unsigned long long* ready, unsigned long long seq) {
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    st_release_sys(ready, seq);
+  }
+}
+__global__ void push_wait_ack_kernel(const unsigned long long* ack, unsigned long long want, unsigned int* status) {
+  if (threadIdx.x == 0) (void)spin_until(ack, want, status);
+}
+}  // namespace ktb
+
+int ktb_push_scatter_ce(int root_dev, const void* src_root, size_t n_elems, size_t granule, int dtype, int n_ranks,
+                        int root_rank, const int* devs, void* const* stage_peer, size_t stage_stride,
+                        void* const* ctrl_peer, void* ctrl_root, size_t chunk_elems, unsigned long long seq,
+                        uintptr_t stream) {
+  int rc = require_device(root_dev);
+  if (rc) return rc;
+  const size_t es = dtype_size(dtype);
+  KTB_REQUIRE(es != 0, KTB_ERR_ARG, "ktb_push_scatter_ce: unknown dtype %d", dtype);
+  KTB_REQUIRE(n_ranks > 0 && n_ranks <= kPushMaxRanks && root_rank >= 0 && root_rank < n_ranks && devs, KTB_ERR_ARG,
+              "ktb_push_scatter_ce: bad ranks %d/%d", root_rank, n_ranks);
+  KTB_REQUIRE(src_root && stage_peer && ctrl_peer && ctrl_root && seq > 0 && chunk_elems > 0, KTB_ERR_ARG,
+              "ktb_push_scatter_ce: null/zero argument");
+  KTB_REQUIRE(granule > 0 && n_elems % granule == 0, KTB_ERR_ARG, "ktb_push_scatter_ce: n_elems not a multiple of granule");
+  size_t b0 = 0, e0 = 0;
+  ktb_shard_bounds(n_elems / granule, n_ranks, 0, &b0, &e0);
+  const size_t n_chunks = std::max<size_t>(1, ((e0 - b0) * granule + chunk_elems - 1) / chunk_elems);
+  KTB_REQUIRE(n_chunks <= KTB_PUSH_MAX_CHUNKS, KTB_ERR_ARG, "ktb_push_scatter_ce: %zu chunks exceed %d", n_chunks,
+              KTB_PUSH_MAX_CHUNKS);
+  KTB_GUARD(root_dev);
+  // one library stream (and fork/join event pair) per destination rank on the root device, created on first use:
+  // every peer's copies ride their own copy-engine queue, chunk-major issue order
+  static std::mutex mu;
+  static cudaStream_t ce_stream[kMaxDevices][kPushMaxRanks] = {};
+  static cudaEvent_t ce_done[kMaxDevices][kPushMaxRanks] = {};
+  static cudaEvent_t ce_start[kMaxDevices] = {};
+  std::lock_guard<std::mutex> lk(mu);   // also serialises concurrent CE scatters of one root (they share the streams)
+  if (!ce_start[root_dev]) KTB_CK(cudaEventCreateWithFlags(&ce_start[root_dev], cudaEventDisableTiming));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* croot = static_cast<uint8_t*>(ctrl_root);
+  unsigned int* status = reinterpret_cast<unsigned int*>(croot + KTB_CTRL_STATUS);
+  const size_t buf_off = (size_t)(seq & 1) * stage_stride;
+  KTB_CK(cudaEventRecord(ce_start[root_dev], st));   // the observations are ready once prior work on `st` is done
+  size_t sb[kPushMaxRanks], sl[kPushMaxRanks];
+  for (int r = 0; r < n_ranks; ++r) {
+    size_t b = 0, e = 0;
+    ktb_shard_bounds(n_elems / granule, n_ranks, r, &b, &e);
+    sb[r] = b * granule;
+    sl[r] = (e - b) * granule;
+    if (r == root_rank) continue;
+    KTB_REQUIRE(stage_peer[r] && ctrl_peer[r], KTB_ERR_ARG, "ktb_push_scatter_ce: rank %d has no staging/control block", r);
+    KTB_REQUIRE(sl[r] * es <= stage_stride, KTB_ERR_ARG, "ktb_push_scatter_ce: shard of rank %d exceeds stage_stride", r);
+    if (!ce_stream[root_dev][r]) {
+      KTB_CK(cudaStreamCreateWithFlags(&ce_stream[root_dev][r], cudaStreamNonBlocking));
+      KTB_CK(cudaEventCreateWithFlags(&ce_done[root_dev][r], cudaEventDisableTiming));
+    }
+    KTB_CK(cudaStreamWaitEvent(ce_stream[root_dev][r], ce_start[root_dev], 0));
+    if (seq > 2) {   // do not overwrite staging half (seq & 1) before the rank consumed call seq-2
+      push_wait_ack_kernel<<<1, 32, 0, ce_stream[root_dev][r]>>>(
+          reinterpret_cast<const unsigned long long*>(croot + KTB_CTRL_ACK) + r, seq - 2, status);
+      KTB_CK(cudaGetLastError());
+    }
+  }
+  for (size_t c = 0; c < n_chunks; ++c) {
+    for (int r = 0; r < n_ranks; ++r) {
+      if (r == root_rank) continue;
+      cudaStream_t cs = ce_stream[root_dev][r];
+      const size_t lo = std::min(sl[r], c * chunk_elems), hi = std::min(sl[r], lo + chunk_elems);
+      if (hi > lo)
+        KTB_CK(cudaMemcpyPeerAsync(static_cast<uint8_t*>(stage_peer[r]) + buf_off + lo * es, devs[r],
+                                   static_cast<const uint8_t*>(src_root) + (sb[r] + lo) * es, root_dev, (hi - lo) * es, cs));
+      unsigned long long* ready =
+          reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ctrl_peer[r]) + KTB_CTRL_READY) + c;
+      push_publish_one_kernel<<<1, 32, 0, cs>>>(ready, seq);   // stream-ordered behind the copy
+      KTB_CK(cudaGetLastError());
+    }
+  }
+  for (int r = 0; r < n_ranks; ++r) {   // the caller's stream "contains" the scatter (src may be reused after it)
+    if (r == root_rank) continue;
+    KTB_CK(cudaEventRecord(ce_done[root_dev][r], ce_stream[root_dev][r]));
+    KTB_CK(cudaStreamWaitEvent(st, ce_done[root_dev][r], 0));
+  }
+  return KTB_OK;
 }
 
 int ktb_push_consume(int dev, int op, int dtype, const void* stage_local, size_t stage_stride, void* dst_root_shard,
@@ -332,7 +423,7 @@ int ktb_push_consume(int dev, int op, int dtype, const void* stage_local, size_t
   const size_t chunk_bytes = per * es, shard_bytes = shard_elems * es;
   const uint32_t tpc = (uint32_t)std::max<size_t>(1, (chunk_bytes + kPushTile - 1) / kPushTile);
   const size_t total = (size_t)tpc * (size_t)n_chunks;
-  const unsigned grid = (unsigned)std::min(total, (size_t)device_info(dev)->sm_count * 8);
+  const unsigned grid = (unsigned)total;   // one tile per CTA (see g_push_scatter_ctas_per_sm)
   uint8_t* d = static_cast<uint8_t*>(dst_root_shard);
 #define KTB_PC(DT, OPC)                                                                                       \
   push_consume_kernel<DT, OPC><<<grid, kPushThreads, 0, st>>>(stage, d, shard_bytes, chunk_bytes, tpc, (uint32_t)n_chunks, p, \

@@ -84,6 +84,8 @@ def _weights_on(dev: int, ws: Sequence[torch.Tensor]) -> List[torch.Tensor]:
     return out
 
 
+SCATTER_ENGINE = "ce"        # "ce": copy engines push the observation chunks; "sm": the persistent scatter kernel
+SCATTER_CTAS_PER_SM = 2
 PUSH_CHUNK_ROWS = 37888      # two waves of 74 CTA pairs x 256 rows: whole waves for the fused layer-2+head kernel
 _push_states = {}
 
@@ -138,8 +140,14 @@ def _mlp_scatter_gather_pushed(obs_root, w1, w2, w3, devs, out_root, bounds, wei
             ws = weights[root]
             mlp_forward(obs_root[b0:e0], ws[0], ws[1], ws[2], out=out_root[b0:e0], device=root, stream=st.side, staged=False)
         st.ev_join.record(st.side)
-        L.call("ktb_push_scatter_chunked", root, obs_root.data_ptr(), obs_root.numel(), d_in, L.BF16, n, 0, st.stage_ptrs,
-               st.stride, st.ctrl_ptrs, st.ctrl[0].data_ptr(), PUSH_CHUNK_ROWS * d_in, 1, seq, int(root_stream.cuda_stream))
+        if SCATTER_ENGINE == "ce":   # copy engines move the rows: the root's SMs stay with its own GEMMs
+            L.call("ktb_push_scatter_ce", root, obs_root.data_ptr(), obs_root.numel(), d_in, L.BF16, n, 0,
+                   L.arr(ctypes.c_int, list(devs)), st.stage_ptrs, st.stride, st.ctrl_ptrs, st.ctrl[0].data_ptr(),
+                   PUSH_CHUNK_ROWS * d_in, seq, int(root_stream.cuda_stream))
+        else:
+            L.call("ktb_push_scatter_chunked", root, obs_root.data_ptr(), obs_root.numel(), d_in, L.BF16, n, 0, st.stage_ptrs,
+                   st.stride, st.ctrl_ptrs, st.ctrl[0].data_ptr(), PUSH_CHUNK_ROWS * d_in, SCATTER_CTAS_PER_SM, seq,
+                   int(root_stream.cuda_stream))
     streams = {d: torch.cuda.current_stream(d) for d in devs[1:]}
     scratch = {d: _scratch_for(d, max(e - b for b, e in bounds), d_hidden) for d in devs[1:]}
 

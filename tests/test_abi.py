@@ -117,5 +117,8 @@ def test_bench_reference_arm_emits_the_contract_line():
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["value"] > 0 and line["config"].get("workload")
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # the unmodified reference when baseline/_ref travelled with the repo (install_reference.py), else the oracle port
+    want_kind = "reference" if os.path.isdir(os.path.join(REPO, "baseline", "_ref", "kubetorch")) else "port"
+    assert line["cpu_baseline"]["kind"] == want_kind and line["cpu_baseline"]["cores"] == os.cpu_count()
+    assert line["config"]["parallelism"] == "dp1" and "64 MiB arg" in line["cpu_baseline"]["sample"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]

@@ -24,6 +24,11 @@ from oracle import cases  # noqa: E402
 
 def main():
     n_gpus = int(sys.argv[1]) if len(sys.argv) > 1 else torch.cuda.device_count()
+    transfer = sys.argv[2] if len(sys.argv) > 2 else "auto"          # auto | pull | push
+    if len(sys.argv) > 3:                                              # ce | sm (engine of the pushed scatter)
+        from kubetorch_b200.device import mlp as _mlp
+
+        _mlp.SCATTER_ENGINE = sys.argv[3]
     shards, rows = 4096, 512
     M = shards * rows
     g = torch.Generator(device="cuda:0").manual_seed(0)
@@ -32,7 +37,7 @@ def main():
     w2 = (torch.randn(1024, 1024, device="cuda:0", generator=g) * 0.02).bfloat16()
     w3 = (torch.randn(64, 1024, device="cuda:0", generator=g) * 0.02).bfloat16()
     policy = kt.mapped("mlp")(_clone(cases.mlp_policy))
-    remote = kt.fn(policy, name="c4-policy").to(kt.Compute(gpus=n_gpus).distribute("b200", workers=1, num_proc=n_gpus))
+    remote = kt.fn(policy, name="c4-policy").to(kt.Compute(gpus=n_gpus).distribute("b200", workers=1, num_proc=n_gpus, transfer=transfer))
     for _ in range(3):
         out = remote(obs, w1, w2, w3, serialization="pickle")
     torch.cuda.synchronize(0)
@@ -57,7 +62,7 @@ def main():
     torch.testing.assert_close(logits[idx].float(), ref.float(), rtol=2**-7, atol=1e-2)
     flop = 2 * (256 * 1024 + 1024 * 1024 + 1024 * 64) * M
     nbytes = M * 256 * 2 + M * 64 * 2
-    print(json.dumps({"what": "c4_rl_rollout", "n_gpus": n_gpus, "ms_per_call": ms, "calls_per_sec": 1e3 / ms,
+    print(json.dumps({"what": "c4_rl_rollout", "n_gpus": n_gpus, "transfer": transfer, "engine": sys.argv[3] if len(sys.argv) > 3 else "default", "ms_per_call": ms, "calls_per_sec": 1e3 / ms,
                       "arg_plus_result_gbps": nbytes / ms / 1e6, "tflops": flop / ms / 1e9, "parity": "ok (2048 rows)", "host_issue_ms_per_call": host_issue_ms,
                       "root_nvlink_gbps_each_way": (n_gpus - 1) / n_gpus * (M * 256 * 2) / ms / 1e6 if n_gpus > 1 else 0}),
           flush=True)

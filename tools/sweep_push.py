@@ -41,7 +41,7 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else torch.cuda.device_count()
     devs = list(range(n))
     ops.ensure_init(devs)
-    for mib in (16, 64, 256, 1024):
+    for mib in (64, 256, 1024):
         elems = (mib << 20) // 4
         x = torch.randn(elems, device="cuda:0")
         y = torch.empty_like(x)
@@ -49,7 +49,7 @@ def main():
         ms = timeit(lambda: ops.scatter_map_gather(x, "scale", 2.0, devices=devs, out_root=y), devs, iters)
         emit(what="c2_device", n_gpus=n, mib=mib, mode="pull_push_fused", ms=ms, gbps=2 * elems * 4 / ms / 1e6,
              ok=bool(torch.equal(y[-4096:].cpu(), x[-4096:].cpu() * 2)))
-        for chunks in (4, 16, 32, 64):
+        for chunks in (8, 16, 32):
             y.zero_()
             sess = ops.PushSession(devs, ops.shard_bounds(elems, n, 0)[1] * 4, n_chunks=chunks)
             ms = timeit(lambda: sess.call(x, y, "scale", 2.0), devs, iters)
@@ -60,7 +60,7 @@ def main():
                  gbps=2 * elems * 4 / ms / 1e6, link_gbps_per_dir=(n - 1) / n * elems * 4 / ms / 1e6, ok=ok)
             del sess
         if mib == 256:
-            for cps in (1, 2, 4, 8, 16):
+            for cps in (4, 8):
                 ops.set_tuning(21, cps)
                 sess = ops.PushSession(devs, ops.shard_bounds(elems, n, 0)[1] * 4, n_chunks=32)
                 ms = timeit(lambda: sess.call(x, y, "scale", 2.0), devs, iters)
