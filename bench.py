@@ -370,7 +370,7 @@ def run_ours(args):
             y_ptr = ops.ipc_open(dev, everyone[0]["y"])
             ctrl_root_ptr = ops.ipc_open(dev, everyone[0]["ctrl"])
         stream = torch.cuda.current_stream(dev).cuda_stream
-        side = torch.cuda.Stream(dev)
+        side, scat = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
         seq_box = [0]
         esize = {L.F32: 4, L.BF16: 2, L.F16: 2, L.U8: 1, L.I64: 8, L.I32: 4}
@@ -389,10 +389,10 @@ def run_ours(args):
             bb, ee = ops.shard_bounds(n // gran, world, rank)
             if rank == 0:
                 cur = torch.cuda.current_stream(dev)
-                if ee > bb:   # fork point BEFORE the scatter launch; the own-shard map is launched after it (side stream)
-                    ev_fork.record(cur)
+                ev_fork.record(cur)           # args ready; the scatter runs on its own stream so that consecutive calls
+                scat.wait_event(ev_fork)      # overlap (the caller's stream carries every call's completion wait)
                 L.call("ktb_push_scatter", dev, x_ptr + off, n, gran, dt, world, 0, c_stage, stride, c_ctrl,
-                       ctrl_root_ptr, n_chunks, seq, stream)
+                       ctrl_root_ptr, n_chunks, seq, scat.cuda_stream)
                 if ee > bb:
                     side.wait_event(ev_fork)
                     L.call("ktb_map", dev, op, dt, x_ptr + off + bb * gran * e_, y_ptr + off + bb * gran * e_,
@@ -633,7 +633,7 @@ def run_ours(args):
             kt.Compute(gpus=n_gpus).distribute("b200", workers=1, num_proc=n_gpus))
         # the caller's pinned buffer, allocated through the framework's NUMA-aware allocator (kt.pinned_empty): shard r's
         # pages live on GPU r's socket.  The result buffer is allocated per call by the framework the same way.
-        xh = kt.pinned_empty((N_ELEMS,), torch.float32, gpus=n_gpus)
+        xh = kt.pinned_empty((N_ELEMS,), torch.float32, module=remote)
         xh.normal_()
         e2e_steps = max(3, min(K, 10))
         for _ in range(3):

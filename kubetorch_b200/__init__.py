@@ -34,14 +34,17 @@ from .resources.inert import Image, Secret, Volume, images, secret  # noqa: F401
 
 
 
-def pinned_empty(shape, dtype=None, gpus=None, devices=None):
-    """Uninitialised PINNED host tensor for host-resident calls.  With `gpus=N` (or explicit `devices`) the pages of
-    `x.chunk(N)[r]` are placed on the NUMA node of GPU r, so a sharded call on `kt.Compute(gpus=N)` moves every shard
-    over its own socket's memory controllers and its own GPU's PCIe link (ktb_host_alloc_sharded)."""
+def pinned_empty(shape, dtype=None, gpus=None, devices=None, module=None):
+    """Uninitialised PINNED host tensor for host-resident calls.  With `module=<deployed kt.fn>` (the GPUs that
+    deployment's ranks run on), `gpus=N` or explicit `devices`, the pages of `x.chunk(N)[r]` are placed on the NUMA node
+    of rank r's GPU, so a sharded call moves every shard over its own socket's memory controllers and its own GPU's
+    PCIe link (ktb_host_alloc_sharded)."""
     import torch
 
     from .device import ops
 
+    if module is not None and getattr(getattr(module, "_supervisor", None), "devices", None):
+        devices = module._supervisor.devices
     devs = list(devices) if devices is not None else (list(range(int(gpus))) if gpus else None)
     return ops.pinned_empty(shape, dtype or torch.float32, devices=devs)
 

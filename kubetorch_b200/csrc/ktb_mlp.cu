@@ -1448,6 +1448,8 @@ size_t ktb_mlp_stage_bytes(size_t M, int d_in) {
   return 2 * rows * (size_t)d_in * 2;
 }
 
+int g_mlp_stage_ce = 1;   // ktb_set_tuning(22, v): staged pulls by copy engine (1) or by a pull kernel (0)
+
 static int mlp_run(int dev, const void* obs, size_t M, int d_in, int d_hidden, int d_out, const void* W1,
                    const void* W2, const void* W3, void* logits, void* scratch, void* stage, uintptr_t stream) {
   int rc = require_device(dev);
@@ -1504,8 +1506,14 @@ static int mlp_run(int dev, const void* obs, size_t M, int d_in, int d_hidden, i
       const int b = (int)(c & 1);
       __nv_bfloat16* dstb = stg + (size_t)b * chunk * d_in;
       if (c >= 2) KTB_CK(cudaStreamWaitEvent(side, evs[3 + b], 0));   // GEMM 1 of chunk c-2 consumed it
-      rc = launch_map(dev, KTB_OP_IDENTITY, KTB_U8, a1, dstb, rows * (size_t)d_in * 2, ident, KTB_VARIANT_AUTO, side);
-      if (rc) return rc;
+      if (g_mlp_stage_ce) {
+        // copy engine pull: no SM of this rank moves observation rows (the persistent GEMM CTAs own the SMs, a pull
+        // KERNEL only gets the gaps between them)
+        KTB_CK(cudaMemcpyAsync(dstb, a1, rows * (size_t)d_in * 2, cudaMemcpyDefault, side));
+      } else {
+        rc = launch_map(dev, KTB_OP_IDENTITY, KTB_U8, a1, dstb, rows * (size_t)d_in * 2, ident, KTB_VARIANT_AUTO, side);
+        if (rc) return rc;
+      }
       KTB_CK(cudaEventRecord(evs[1 + b], side));
       KTB_CK(cudaStreamWaitEvent(st, evs[1 + b], 0));
       a1 = dstb;

@@ -369,7 +369,108 @@ def rm(key: str, recursive: bool = False, verbose: bool = False, namespace: Opti
 
 
 # ---- BroadcastWindow quorum (threads of the controller process) ------------------------------------------------
+def _join_shared(key: str, leaves, bw: BroadcastWindow, role: str):
+    """BroadcastWindow ACROSS rank processes (the reference's real usage: every pod joins the same window,
+    kt/data_store/pod_data_server.py:1172-1341).  The rendezvous is a directory under KTB_STORE_DIR (the stand-in for
+    the metadata server): every participant drops a join file, the window closes when `world_size` joined (or, for a
+    timeout-only window, at the deadline with at least one putter and one getter); getters then pull the putter's
+    leaves out of its IPC-exported arenas with the segmented kernel on their own GPU and drop a done file, the putter
+    returns once every getter is done.  A window that cannot close raises DataStoreError on every participant and
+    leaves no state behind, so the next window with the same group id works (the reference's fault-injection case,
+    tests/assets/kv_store/gpu_helper.py:607-670)."""
+    import uuid
+
+    import torch
+
+    gid = bw.group_id or f"auto:{key}"
+    gdir = os.path.join(_store_dir(), "bw_" + hashlib.sha1(gid.encode()).hexdigest())
+    os.makedirs(gdir, exist_ok=True)
+    me = f"{time.time_ns():020d}_{role}_{os.getpid()}_{uuid.uuid4().hex[:8]}"
+    mine = os.path.join(gdir, me + ".join")
+    with open(mine + ".tmp", "w") as f:
+        json.dump({"role": role, "key": key, "leaves": [tk for tk, _ in leaves], "pid": os.getpid()}, f)
+    os.replace(mine + ".tmp", mine)
+    deadline = time.time() + (bw.timeout if bw.timeout is not None else 600.0)
+
+    def members():
+        out = []
+        for name in sorted(os.listdir(gdir)):
+            if name.endswith(".join"):
+                try:
+                    with open(os.path.join(gdir, name)) as f:
+                        out.append((name[:-5], json.load(f)))
+                except (OSError, ValueError):
+                    pass
+        return out
+
+    def leave():
+        for suffix in (".join", ".done"):
+            try:
+                os.remove(os.path.join(gdir, me + suffix))
+            except OSError:
+                pass
+
+    closed = os.path.join(gdir, "CLOSED")
+    while True:
+        mem = members()
+        n_put = sum(1 for _, m in mem if m["role"] == "put")
+        n_get = len(mem) - n_put
+        if os.path.exists(closed):
+            break
+        if bw.world_size is not None and len(mem) >= bw.world_size:
+            break
+        if time.time() >= deadline:
+            if bw.world_size is None and n_put and n_get:
+                break                                    # a timeout-only window closes at its deadline
+            leave()
+            raise DataStoreError(f"BroadcastWindow '{gid}' timed out with {n_put} putter(s) and {n_get} getter(s)")
+        time.sleep(0.002)
+    try:
+        open(closed, "a").close()                        # late joiners of THIS window see it closed and proceed
+        mem = members()
+        names = [name for name, _ in mem]
+        rank = names.index(me) if me in names else len(names)
+        if not any(m["role"] == "put" for _, m in mem):
+            raise DataStoreError("BroadcastWindow closed without a putter")
+        getters = [name for name, m in mem if m["role"] == "get"]
+        if role == "get":
+            pairs = []
+            for tk, dst in leaves:
+                fk = _full_key(key, tk)
+                with _lock:
+                    ent = _registry.get(fk)
+                src = (ent.tensor, ent.event) if ent is not None else (_lookup_shared(fk), None)
+                if src[0] is None:
+                    raise DataStoreError(f"Key '{fk}' was not published in this broadcast group")
+                _check_pair(fk, src[0], dst)
+                pairs.append((src[0], src[1], dst))
+            _pull(pairs)
+            for dev in {d.device.index for _, d in leaves}:
+                torch.cuda.synchronize(dev)              # the bytes are in the destination before "done" is visible
+            open(os.path.join(gdir, me + ".done"), "a").close()
+        else:
+            while True:                                  # the source must stay valid until every getter has pulled
+                done = {n[:-5] for n in os.listdir(gdir) if n.endswith(".done")}
+                if all(g in done for g in getters):
+                    break
+                if time.time() >= deadline + 30.0:
+                    raise DataStoreError(f"BroadcastWindow '{gid}': getters did not finish pulling")
+                time.sleep(0.002)
+        return {"rank": rank, "world_size": len(mem), "group_id": gid, "role": role}
+    finally:
+        if role == "put":                                # the putter is the last one out: clear the window's state
+            for name in os.listdir(gdir):
+                try:
+                    os.remove(os.path.join(gdir, name))
+                except OSError:
+                    pass
+        elif not os.path.exists(os.path.join(gdir, me + ".done")):
+            leave()
+
+
 def _join(key: str, leaves, bw: BroadcastWindow, role: str):
+    if _store_dir() is not None:
+        return _join_shared(key, leaves, bw, role)
     gid = bw.group_id or f"auto:{key}"
     with _lock:
         grp = _groups.get(gid)

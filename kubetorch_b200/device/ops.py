@@ -528,6 +528,13 @@ class PushSession:
         # host mirror of every control block's sticky status word, refreshed by an async D2H copy behind each call:
         # a timed-out in-kernel wait is seen at the NEXT call without a host sync on the data path
         self._side = torch.cuda.Stream(self.root)       # the root's own shard maps beside the scatter, not behind it
+        # the scatter itself runs on an internal stream ordered only behind "args ready": the caller's stream carries
+        # the completion wait of every call, so call k+1's scatter starts while call k's last chunk is still coming
+        # back (the staging halves are protected by the in-kernel ack wait, not by stream order)
+        self._scatter_stream = torch.cuda.Stream(self.root)
+        # ... only when every rank has its own GPU: ranks time-sliced on the root's GPU (1-GPU test boxes) could find
+        # their consume kernels queued behind a later call's spinning scatter CTAs
+        self._overlap_calls = len(set(self.devices)) == len(self.devices)
         self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
         self._status_host = torch.zeros(n, dtype=torch.int32).pin_memory()
         self._status_dev = [c[1032:1036].view(torch.int32) for c in self.ctrl]
@@ -547,14 +554,21 @@ class PushSession:
         root_stream = _stream(self.root, None)
         b, e = shard_bounds(rows, n, 0)  # the root's own shard maps on the root's HBM, on a side stream
         own = e > b
-        if own:   # the fork point is recorded BEFORE the scatter launch (an event recorded after it would order the side
-            # stream behind the whole scatter) ...
-            with torch.cuda.device(self.root):
-                self._ev_fork.record(torch.cuda.current_stream(self.root))
+        with torch.cuda.device(self.root):
+            # fork point: args ready and the result buffer allocated (recorded BEFORE the scatter launch — an event
+            # recorded after it would order the side stream behind the whole scatter)
+            self._ev_fork.record(torch.cuda.current_stream(self.root))
+            if self._overlap_calls:
+                self._scatter_stream.wait_event(self._ev_fork)
+                scatter_stream = int(self._scatter_stream.cuda_stream)
+                x_root.record_stream(self._scatter_stream)
+            else:
+                scatter_stream = root_stream
         L.call("ktb_push_scatter", self.root, x_root.data_ptr(), x_root.numel(), gran, dt, n, 0, self._stage_ptrs,
-               self.stride, self._ctrl_ptrs, self.ctrl[0].data_ptr(), self.n_chunks, seq, root_stream)
-        if own:   # ... but the map kernel is LAUNCHED after the scatter: the scatter's persistent CTAs (a few per SM) take
-            # their slots first and the HBM-bound map fills the rest, instead of the scatter queueing behind 8192 map CTAs
+               self.stride, self._ctrl_ptrs, self.ctrl[0].data_ptr(), self.n_chunks, seq, scatter_stream)
+        if own:   # ... but the map kernel is LAUNCHED after the scatter: the scatter's CTAs reach the SMs first and the ranks
+            # get their first chunk without waiting for the root's own shard (measured: map-first delays the scatter by
+            # the whole map, 41 us at N = 2); the HBM-bound map then drains beside the scatter's tail
             with torch.cuda.device(self.root):
                 self._side.wait_event(self._ev_fork)
                 L.call("ktb_map", self.root, OPS[op], dt, x_root.data_ptr() + b * gran * es,

@@ -172,6 +172,52 @@ def store_get_from_rank(src_rank, n):
     return [float(dest.sum()), kt.ls("by-rank")]
 
 
+def store_broadcast(n, world_size, timeout=30.0, group_id="bw-ranks"):
+    """One BroadcastWindow across the rank processes (tests/assets/kv_store/gpu_helper.py broadcast patterns): rank 0
+    puts a state dict, every other rank gets it into its own GPU tensors; returns this rank's view."""
+    import torch
+
+    import kubetorch_b200 as kt
+
+    r, _ = _rank_world()
+    dev = f"cuda:{torch.cuda.current_device()}"
+    bw = kt.BroadcastWindow(world_size=world_size, timeout=timeout, group_id=group_id)
+    if r == 0:
+        sd = {"w": torch.arange(n, dtype=torch.float32, device=dev) * 0.5, "b": torch.full((7,), 3, dtype=torch.int64, device=dev)}
+        _KEEP.append(sd)
+        info = kt.put(key="bw/sd", src=sd, broadcast=bw)
+        return {"role": "put", "world": info["world_size"], "sum": float(sd["w"].sum()), "b": sd["b"].tolist()}
+    dest = {"w": torch.zeros(n, dtype=torch.float32, device=dev), "b": torch.zeros(7, dtype=torch.int64, device=dev)}
+    info = kt.get(key="bw/sd", dest=dest, broadcast=bw)
+    torch.cuda.synchronize()
+    return {"role": "get", "world": info["world_size"], "sum": float(dest["w"].sum()), "b": dest["b"].tolist()}
+
+
+def store_broadcast_without_putter(timeout=0.3, group_id="bw-ranks"):
+    """The fault case (gpu_helper.py:607-670): a window that can never close fails with a timeout on every
+    participant ... and the store stays usable (the caller runs store_broadcast on the same group right after)."""
+    import torch
+
+    import kubetorch_b200 as kt
+
+    dest = torch.zeros(4, device=f"cuda:{torch.cuda.current_device()}")
+    try:
+        kt.get(key="bw/never", dest=dest, broadcast=kt.BroadcastWindow(world_size=99, timeout=timeout, group_id=group_id))
+    except kt.DataStoreError as e:
+        return {"expected_failure": True, "error": str(e)}
+    return {"expected_failure": False}
+
+
+class StoreWindows:
+    """Both window patterns on ONE deployment (one store): the fault case first, then real broadcasts."""
+
+    def fault(self, timeout=0.3, group_id="bw-ranks"):
+        return store_broadcast_without_putter(timeout, group_id)
+
+    def broadcast(self, n, world_size, timeout=30.0, group_id="bw-ranks"):
+        return store_broadcast(n, world_size, timeout, group_id)
+
+
 _KEEP = []
 
 

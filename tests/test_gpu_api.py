@@ -572,7 +572,7 @@ def test_small_call_lane_is_indistinguishable_from_the_general_path(golden):
         lane = _deploy(double, world, f"t-lane-{world}", placement="auto")
         spread = _deploy(double, world, f"t-spread-{world}", placement="ranks")
         try:
-            assert lane._fast is not None and spread._fast is None
+            assert lane._fast is not None and (spread._fast is None) == (world > 1)   # 1 rank: nothing to spread
             for name in ("f32_1003", "f32_3", "bf16_777", "i64_130", "i32_515"):
                 x = golden["all_inputs"][name]
                 want = ref_dispatch.spmd_call(cases.double, x, num_proc=world, serialization="pickle")
@@ -613,3 +613,26 @@ def test_small_call_lane_is_indistinguishable_from_the_general_path(golden):
         assert torch.equal(torch.cat(r(torch.arange(10.0).cuda(), serialization="pickle")).cpu(), torch.arange(10.0) * 0.5)
     finally:
         r.teardown()
+
+
+def test_broadcast_window_across_rank_processes_and_the_timeout_fault_case():
+    """(f1) BroadcastWindow with participants in DIFFERENT rank processes (file rendezvous under KTB_STORE_DIR + CUDA-IPC
+    arenas), and the reference's fault-injection pattern: a receive that can never complete fails with a timeout,
+    leaves nothing behind, and the very next window on the same group id works (gpu_helper.py:607-670)."""
+    n_dev = torch.cuda.device_count()
+    world = 3
+    devices = [r % n_dev for r in range(world)]
+    comp = kt.Compute(gpus=1, allowed_serialization=["json", "pickle"]).distribute(
+        "spmd", workers=1, num_proc=world, devices=devices)
+    win = kt.cls(cases.StoreWindows, name="t-bw-ranks").to(comp)
+    try:
+        out = win.fault(0.3, "bw-shared", serialization="pickle")
+        assert all(o["expected_failure"] and "timed out with 0 putter(s) and 3 getter(s)" in o["error"] for o in out), out
+        for it in range(2):                       # same store, same group id as the failed window, twice
+            n = 100_003 + it
+            out = win.broadcast(n, world, 30.0, "bw-shared", serialization="pickle")
+            want = float((torch.arange(n, dtype=torch.float32) * 0.5).sum())
+            assert [o["role"] for o in out] == ["put", "get", "get"]
+            assert all(o["world"] == world and o["b"] == [3] * 7 and o["sum"] == want for o in out), out
+    finally:
+        win.teardown()

@@ -38,9 +38,19 @@ def timeit(fn, devs, iters):
 
 
 def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else torch.cuda.device_count()
+    n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else torch.cuda.device_count()
     devs = list(range(n))
     ops.ensure_init(devs)
+    if "--one" in sys.argv:      # a few calls of the shipped configuration, for ncu
+        elems = (256 << 20) // 4
+        x = torch.randn(elems, device="cuda:0")
+        y = torch.empty_like(x)
+        sess = ops.PushSession(devs, ops.shard_bounds(elems, n, 0)[1] * 4)
+        for _ in range(3):
+            sess.call(x, y, "scale", 2.0)
+        for d in devs:
+            torch.cuda.synchronize(d)
+        return
     for mib in (64, 256, 1024):
         elems = (mib << 20) // 4
         x = torch.randn(elems, device="cuda:0")
