@@ -339,14 +339,18 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// Spin until *flag >= want. Returns false on timeout (and records it in *status).
+// Spin until *flag >= want. Returns false on timeout (and records it in *status).  The limit is the u64 that follows
+// the status word in the control block (KTB_CTRL_TIMEOUT_NS; 0 = the 10 s default) — read on the slow path only.
 __device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long want,
                                            unsigned int* status) {
   if (ld_acquire_sys(flag) >= want) return true;
+  unsigned long long limit =
+      *reinterpret_cast<const volatile unsigned long long*>(reinterpret_cast<const char*>(status) + 8);
+  if (limit == 0) limit = kSpinTimeoutNs;
   const unsigned long long t0 = globaltimer_ns();
   while (ld_acquire_sys(flag) < want) {
     __nanosleep(200);
-    if (globaltimer_ns() - t0 > kSpinTimeoutNs) {
+    if (globaltimer_ns() - t0 > limit) {
       atomicExch(status, 1u);
       return false;
     }
@@ -366,6 +370,7 @@ __device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsig
 #define KTB_CTRL_ACK 512
 #define KTB_CTRL_TICKET 1024
 #define KTB_CTRL_STATUS 1032
+#define KTB_CTRL_TIMEOUT_NS 1040   /* u64 after the status word: spin limit in ns, 0 = 10 s */
 #define KTB_CTRL_CHUNK_DONE 2048
 #define KTB_PUSH_MAX_CHUNKS 64
 

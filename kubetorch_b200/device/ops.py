@@ -592,6 +592,13 @@ class PushSession:
                 self._status_host[r:r + 1].copy_(self._status_dev[r], non_blocking=True)
         return out_root
 
+    def set_spin_timeout(self, seconds: float) -> None:
+        """In-kernel flag waits give up after `seconds` (default 10 s) and raise the sticky status word."""
+        ns = torch.tensor([int(seconds * 1e9)], dtype=torch.int64)
+        for d, c in zip(self.devices, self.ctrl):
+            c[1040:1048].view(torch.int64).copy_(ns.to(f"cuda:{d}"))
+            torch.cuda.synchronize(d)
+
     def check(self):
         for d, c in zip(self.devices, self.ctrl):
             st = ctypes.c_uint(0)

@@ -636,3 +636,36 @@ def test_broadcast_window_across_rank_processes_and_the_timeout_fault_case():
             assert all(o["world"] == world and o["b"] == [3] * 7 and o["sum"] == want for o in out), out
     finally:
         win.teardown()
+
+
+def test_device_stall_maps_to_pod_terminated_error():
+    """A rank whose piece never arrives (its peer stalled or died): the in-kernel wait gives up, the consume kernel stores
+    NOTHING, the sticky status word reaches the host behind the next call and the caller gets the reference's
+    PodTerminatedError (kt/serving/utils.py:111-190), not stale bytes."""
+    import ctypes
+
+    from kubetorch_b200.device import lib as L
+    from kubetorch_b200.device import ops
+
+    double = _mapped(cases.double, "scale", alpha=2.0)
+    remote = kt.fn(double, name="t-stall").to(
+        kt.Compute(gpus=1, allowed_serialization=["json", "pickle"]).distribute(
+            "b200", workers=1, num_proc=2, devices=[0, 0], placement="ranks", transfer="push"))
+    try:
+        x = torch.arange(1 << 16, dtype=torch.float32).cuda()
+        assert torch.equal(torch.cat(remote(x, serialization="pickle")).cpu(), x.cpu() * 2)
+        sup = remote._supervisor
+        sess = sup._push
+        sess.set_spin_timeout(0.05)
+        # sabotage: rank 1 is asked to consume call seq+1, which the root never scatters
+        sentinel = torch.full((1 << 15,), -1.0, device="cuda:0")
+        L.call("ktb_push_consume", 0, L.OP_SCALE, L.F32, sess.stage[1].data_ptr(), sess.stride, sentinel.data_ptr(),
+               sentinel.numel(), 2.0, 0.0, sess.ctrl[1].data_ptr(), sess.ctrl[0].data_ptr(), 1, sess.n_chunks,
+               ctypes.c_ulonglong(sess.seq + 1000), ops.current_stream_handle(0))
+        torch.cuda.synchronize(0)
+        assert bool((sentinel == -1.0).all())                     # a timed-out consumer writes nothing
+        with pytest.raises(kt.PodTerminatedError) as ei:
+            sup.check_device_health()
+        assert ei.value.reason == "DeviceTimeout" and ei.value.status_code == 503
+    finally:
+        remote.teardown()
