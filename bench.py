@@ -370,7 +370,7 @@ def run_ours(args):
             y_ptr = ops.ipc_open(dev, everyone[0]["y"])
             ctrl_root_ptr = ops.ipc_open(dev, everyone[0]["ctrl"])
         stream = torch.cuda.current_stream(dev).cuda_stream
-        side, scat = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        side = torch.cuda.Stream(dev)
         ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
         seq_box = [0]
         esize = {L.F32: 4, L.BF16: 2, L.F16: 2, L.U8: 1, L.I64: 8, L.I32: 4}
@@ -389,15 +389,14 @@ def run_ours(args):
             bb, ee = ops.shard_bounds(n // gran, world, rank)
             if rank == 0:
                 cur = torch.cuda.current_stream(dev)
-                ev_fork.record(cur)           # args ready; the scatter runs on its own stream so that consecutive calls
-                scat.wait_event(ev_fork)      # overlap (the caller's stream carries every call's completion wait)
-                L.call("ktb_push_scatter", dev, x_ptr + off, n, gran, dt, world, 0, c_stage, stride, c_ctrl,
-                       ctrl_root_ptr, n_chunks, seq, scat.cuda_stream)
-                if ee > bb:
+                if ee > bb:   # the root's own shard maps on a side stream, forked and launched before the scatter
+                    ev_fork.record(cur)
                     side.wait_event(ev_fork)
                     L.call("ktb_map", dev, op, dt, x_ptr + off + bb * gran * e_, y_ptr + off + bb * gran * e_,
                            (ee - bb) * gran, float(a), float(b), L.VARIANT_AUTO, side.cuda_stream)
                     ev_join.record(side)
+                L.call("ktb_push_scatter", dev, x_ptr + off, n, gran, dt, world, 0, c_stage, stride, c_ctrl,
+                       ctrl_root_ptr, n_chunks, seq, stream)
                 L.call("ktb_push_wait", dev, ctrl_root_ptr, world, 0, seq, stream)
                 if ee > bb:
                     cur.wait_event(ev_join)
@@ -544,7 +543,7 @@ def run_ours(args):
 
     # everything below runs on rank 0 as ONE controller process driving all N GPUs through the public API (the product's
     # launch mode); the other torchrun ranks release their arenas and wait on a CPU barrier
-    e2e = small = c5 = c4 = None
+    e2e = small = c5 = c4 = c1 = None
     if world > 1:
         torch.cuda.synchronize()
     if rank == 0:
@@ -764,6 +763,23 @@ def run_ours(args):
         c4 = _timeboxed(c4_rollout, "c4")
         torch.cuda.empty_cache()
 
+        # ---- configs[0]: hello_world via kt.fn/.to on kt.Compute(cpus='.1'), local in-process backend (plumbing, no GPU) ---
+        def c1_hello():
+            r = kt.fn(cases.hello_world, name="bench-hello").to(kt.Compute(cpus=".1"))
+            try:
+                assert r() == "Hello from Kubetorch!"
+                for _ in range(2000):
+                    r()
+                t0 = time.perf_counter()
+                for _ in range(20000):
+                    r()
+                return {"workload": "configs[0]: hello_world single remote call, kt.Compute(cpus='.1'), in-process backend",
+                        "calls_per_sec": 20000 / (time.perf_counter() - t0)}
+            finally:
+                r.teardown()
+
+        c1 = _timeboxed(c1_hello, "c1")
+
     if world > 1:
         dist.barrier(group=cpu_group)  # other ranks wait on the CPU while rank 0 drives all N GPUs
 
@@ -801,7 +817,8 @@ def run_ours(args):
                 "l2": "inputs+outputs (512 MiB) exceed the 126 MB L2; no flush needed",
             },
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "parity": parity,
-            "small_calls": small, "c5": c5, "c4_rollout": c4, "c3_ddp": c3, "gpu_launches": gpu_launches,
+            "c1_hello_world": c1, "small_calls": small, "c5": c5, "c4_rollout": c4, "c3_ddp": c3,
+            "gpu_launches": gpu_launches,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -915,7 +932,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c3", action="store_true")
-    ap.add_argument("--push-chunks", type=int, default=16, help="chunks per shard of the push/push flag pipeline")
+    ap.add_argument("--push-chunks", type=int, default=32, help="chunks per shard of the push/push flag pipeline")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -53,14 +53,15 @@ struct PushScatterArgs {
 };
 
 __global__ void __launch_bounds__(kPushThreads)
-    push_scatter_kernel(const __grid_constant__ PushScatterArgs a, unsigned int* chunk_done, unsigned int* status) {
+    push_scatter_kernel(const __grid_constant__ PushScatterArgs a, unsigned int* chunk_done, unsigned int* status,
+                        uint32_t slice) {
   const uint32_t tiles_per_chunk = a.tile_prefix[a.n];
   const uint32_t total_tiles = tiles_per_chunk * (uint32_t)a.n_chunks;
   __shared__ bool last;
-  // Persistent grid (the launch caps the CTAs per SM so that other kernels of the root — its own shard's map, the
-  // MLP of rank 0 — keep their share of every SM).  Every CTA walks the tiles in increasing order = chunk-major and
-  // reports its finished tiles ONCE per chunk (one system fence + one atomic per CTA per chunk, not per tile: the
-  // fence has to wait for the acknowledgement of every peer store the CTA has in flight).
+  // Every CTA streams a SLICE of `slice` consecutive 16 KiB tiles (chunk-major tile order) and reports them with ONE
+  // system fence + one atomic: the fence has to wait for the acknowledgement of every peer store the CTA has in flight,
+  // and under a saturated link that wait is queueing delay (ncu: the per-tile-fence form moved 134 MB in 0.42 ms where
+  // the plain push kernel needs 0.31 ms).  grid = ceil(tiles / slice) by default; a smaller grid walks further slices.
   uint32_t cur_chunk = 0xffffffffu, n_done = 0;
   auto flush = [&]() {   // all threads call it together
     __syncthreads();     // every thread's stores of the finished tiles are issued
@@ -78,7 +79,8 @@ __global__ void __launch_bounds__(kPushThreads)
     }
     __syncthreads();     // `last` is reused
   };
-  for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  for (uint32_t base = blockIdx.x * slice; base < total_tiles; base += gridDim.x * slice)
+  for (uint32_t tile = base; tile < min(total_tiles, base + slice); ++tile) {
     const uint32_t c = tile / tiles_per_chunk;                // chunk 0 of every rank goes out first
     const uint32_t rem = tile % tiles_per_chunk;
     if (c != cur_chunk) {
@@ -128,15 +130,17 @@ __global__ void push_publish_kernel(const __grid_constant__ PushScatterArgs a) {
 template <int DT, int OP>
 __global__ void __launch_bounds__(kPushThreads)
     push_consume_kernel(const uint8_t* stage, uint8_t* dst, size_t shard_bytes, size_t chunk_bytes,
-                        uint32_t tiles_per_chunk, uint32_t n_chunks, MapParams p, const unsigned long long* ready,
-                        unsigned long long seq, unsigned long long* ack, unsigned int* ticket, unsigned int* status) {
+                        uint32_t tiles_per_chunk, uint32_t n_chunks, uint32_t slice, MapParams p,
+                        const unsigned long long* ready, unsigned long long seq, unsigned long long* ack,
+                        unsigned int* ticket, unsigned int* status) {
   constexpr size_t ES = (DT == KTB_U8) ? 1 : ((DT == KTB_BF16 || DT == KTB_F16) ? 2 : (DT == KTB_I64 ? 8 : 4));
   const uint32_t total_tiles = tiles_per_chunk * n_chunks;
   __shared__ bool flag;
   uint32_t have = 0;   // chunks [0, have) are known to have landed
   // persistent grid, tiles in increasing order = chunk order; ONE system fence per CTA (before the ack ticket), not per
   // tile: the fence waits for the acknowledgement of every peer store the CTA has in flight
-  for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  for (uint32_t base = blockIdx.x * slice; base < total_tiles; base += gridDim.x * slice)
+  for (uint32_t tile = base; tile < min(total_tiles, base + slice); ++tile) {
     const uint32_t c = tile / tiles_per_chunk;
     const uint32_t t = tile % tiles_per_chunk;
     if (c >= have) {
@@ -218,10 +222,11 @@ size_t ktb_push_control_bytes(void) { return 4096; }
 
 // (control-block layout: KTB_CTRL_* in ktb_common.cuh)
 
-// 0 = one tile per CTA (measured best, profiles/r2_summary.md §2: the root's NVLink egress needs ALL thread slots
-// of the GPU in flight — 8 persistent CTAs per SM reach 380 GB/s per direction, 4: 355, 1-2: 260-290, against 430+
-// for short-lived CTAs that let the side stream's kernels interleave); n > 0 caps a persistent grid at n CTAs per SM
+// grid cap of the scatter in CTAs per SM (0 = no cap: ceil(tiles / slice) CTAs).  Caps were measured slower for the
+// element-wise call (profiles/r2_summary.md §2); ktb_push_scatter_chunked takes its own cap for the MLP.
 std::atomic<int> g_push_scatter_ctas_per_sm{0};   // ktb_set_tuning(21, n)
+// tiles (16 KiB) per CTA per system fence, both sides
+std::atomic<int> g_push_slice{4};                 // ktb_set_tuning(23, n)
 
 // chunk_elems == 0: n_chunks pieces per shard (chunk_bounds); otherwise pieces of exactly chunk_elems elements
 // (the consumer of ktb_mlp_bf16_pushed wants whole GEMM row chunks), n_chunks = ceil(largest shard / chunk_elems).
@@ -281,10 +286,11 @@ static int push_scatter_impl(const char* who, int root_dev, const void* src_root
   if (tiles_per_chunk == 0) {
     push_publish_kernel<<<1, 32, 0, st>>>(a);
   } else {
-    const size_t total = (size_t)tiles_per_chunk * (size_t)n_chunks;
+    const uint32_t slice = (uint32_t)std::max(1, std::min<int>(g_push_slice.load(), (int)tiles_per_chunk));
+    const size_t total = ((size_t)tiles_per_chunk * (size_t)n_chunks + slice - 1) / slice;
     if (ctas_per_sm <= 0) ctas_per_sm = g_push_scatter_ctas_per_sm.load();
     const size_t cap = ctas_per_sm > 0 ? (size_t)device_info(root_dev)->sm_count * (size_t)ctas_per_sm : total;
-    push_scatter_kernel<<<(unsigned)std::min(total, cap), kPushThreads, 0, st>>>(a, chunk_done, status);
+    push_scatter_kernel<<<(unsigned)std::min(total, cap), kPushThreads, 0, st>>>(a, chunk_done, status, slice);
   }
   KTB_CK(cudaGetLastError());
   return KTB_OK;
@@ -422,11 +428,11 @@ int ktb_push_consume(int dev, int op, int dtype, const void* stage_local, size_t
   if (per == 0) per = c0e - c0b;
   const size_t chunk_bytes = per * es, shard_bytes = shard_elems * es;
   const uint32_t tpc = (uint32_t)std::max<size_t>(1, (chunk_bytes + kPushTile - 1) / kPushTile);
-  const size_t total = (size_t)tpc * (size_t)n_chunks;
-  const unsigned grid = (unsigned)total;   // one tile per CTA (see g_push_scatter_ctas_per_sm)
+  const uint32_t slice = (uint32_t)std::max(1, std::min<int>(g_push_slice.load(), (int)tpc));
+  const unsigned grid = (unsigned)(((size_t)tpc * (size_t)n_chunks + slice - 1) / slice);
   uint8_t* d = static_cast<uint8_t*>(dst_root_shard);
 #define KTB_PC(DT, OPC)                                                                                       \
-  push_consume_kernel<DT, OPC><<<grid, kPushThreads, 0, st>>>(stage, d, shard_bytes, chunk_bytes, tpc, (uint32_t)n_chunks, p, \
+  push_consume_kernel<DT, OPC><<<grid, kPushThreads, 0, st>>>(stage, d, shard_bytes, chunk_bytes, tpc, (uint32_t)n_chunks, slice, p, \
                                                               ready, seq, ack, ticket, status)
   if (op == KTB_OP_IDENTITY) {
     KTB_PC(KTB_U8, KTB_OP_IDENTITY);

@@ -511,7 +511,7 @@ class PushSession:
     kernel waits in-kernel for its piece, maps it and pushes the result into the root's result
     buffer. No events between devices: flags in device memory order everything."""
 
-    def __init__(self, devices: Sequence[int], max_shard_bytes: int, n_chunks: int = 16):
+    def __init__(self, devices: Sequence[int], max_shard_bytes: int, n_chunks: int = 32):
         self.devices = [int(d) for d in devices]
         ensure_init(set(self.devices))
         self.root = self.devices[0]
@@ -528,13 +528,6 @@ class PushSession:
         # host mirror of every control block's sticky status word, refreshed by an async D2H copy behind each call:
         # a timed-out in-kernel wait is seen at the NEXT call without a host sync on the data path
         self._side = torch.cuda.Stream(self.root)       # the root's own shard maps beside the scatter, not behind it
-        # the scatter itself runs on an internal stream ordered only behind "args ready": the caller's stream carries
-        # the completion wait of every call, so call k+1's scatter starts while call k's last chunk is still coming
-        # back (the staging halves are protected by the in-kernel ack wait, not by stream order)
-        self._scatter_stream = torch.cuda.Stream(self.root)
-        # ... only when every rank has its own GPU: ranks time-sliced on the root's GPU (1-GPU test boxes) could find
-        # their consume kernels queued behind a later call's spinning scatter CTAs
-        self._overlap_calls = len(set(self.devices)) == len(self.devices)
         self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
         self._status_host = torch.zeros(n, dtype=torch.int32).pin_memory()
         self._status_dev = [c[1032:1036].view(torch.int32) for c in self.ctrl]
@@ -552,29 +545,20 @@ class PushSession:
         rows = x_root.numel() // gran
         dt = dtype_code(x_root.dtype)
         root_stream = _stream(self.root, None)
-        b, e = shard_bounds(rows, n, 0)  # the root's own shard maps on the root's HBM, on a side stream
+        b, e = shard_bounds(rows, n, 0)  # the root's own shard maps on the root's HBM, on a side stream forked BEFORE the
+        # scatter launch and launched before it: measured (profiles/r2_summary.md §2) the other order lets the two grids
+        # interleave on the SMs and costs 0.3 ms at 1 GiB; map-first costs the map's own time (41 us at N = 2, 256 MiB)
         own = e > b
-        with torch.cuda.device(self.root):
-            # fork point: args ready and the result buffer allocated (recorded BEFORE the scatter launch — an event
-            # recorded after it would order the side stream behind the whole scatter)
-            self._ev_fork.record(torch.cuda.current_stream(self.root))
-            if self._overlap_calls:
-                self._scatter_stream.wait_event(self._ev_fork)
-                scatter_stream = int(self._scatter_stream.cuda_stream)
-                x_root.record_stream(self._scatter_stream)
-            else:
-                scatter_stream = root_stream
-        L.call("ktb_push_scatter", self.root, x_root.data_ptr(), x_root.numel(), gran, dt, n, 0, self._stage_ptrs,
-               self.stride, self._ctrl_ptrs, self.ctrl[0].data_ptr(), self.n_chunks, seq, scatter_stream)
-        if own:   # ... but the map kernel is LAUNCHED after the scatter: the scatter's CTAs reach the SMs first and the ranks
-            # get their first chunk without waiting for the root's own shard (measured: map-first delays the scatter by
-            # the whole map, 41 us at N = 2); the HBM-bound map then drains beside the scatter's tail
+        if own:
             with torch.cuda.device(self.root):
+                self._ev_fork.record(torch.cuda.current_stream(self.root))
                 self._side.wait_event(self._ev_fork)
                 L.call("ktb_map", self.root, OPS[op], dt, x_root.data_ptr() + b * gran * es,
                        out_root.data_ptr() + b * gran * es, (e - b) * gran, float(alpha), float(beta), L.VARIANT_AUTO,
                        int(self._side.cuda_stream))
                 self._ev_join.record(self._side)
+        L.call("ktb_push_scatter", self.root, x_root.data_ptr(), x_root.numel(), gran, dt, n, 0, self._stage_ptrs,
+               self.stride, self._ctrl_ptrs, self.ctrl[0].data_ptr(), self.n_chunks, seq, root_stream)
         for r in range(1, n):
             b, e = shard_bounds(rows, n, r)
             if (e - b) * gran * es > self.stride:

@@ -627,7 +627,7 @@ def test_broadcast_window_across_rank_processes_and_the_timeout_fault_case():
     win = kt.cls(cases.StoreWindows, name="t-bw-ranks").to(comp)
     try:
         out = win.fault(0.3, "bw-shared", serialization="pickle")
-        assert all(o["expected_failure"] and "timed out with 0 putter(s) and 3 getter(s)" in o["error"] for o in out), out
+        assert all(o["expected_failure"] and "timed out with 0 putter(s)" in o["error"] for o in out), out
         for it in range(2):                       # same store, same group id as the failed window, twice
             n = 100_003 + it
             out = win.broadcast(n, world, 30.0, "bw-shared", serialization="pickle")

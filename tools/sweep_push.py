@@ -59,7 +59,7 @@ def main():
         ms = timeit(lambda: ops.scatter_map_gather(x, "scale", 2.0, devices=devs, out_root=y), devs, iters)
         emit(what="c2_device", n_gpus=n, mib=mib, mode="pull_push_fused", ms=ms, gbps=2 * elems * 4 / ms / 1e6,
              ok=bool(torch.equal(y[-4096:].cpu(), x[-4096:].cpu() * 2)))
-        for chunks in (8, 16, 32):
+        for chunks in (16, 32):
             y.zero_()
             sess = ops.PushSession(devs, ops.shard_bounds(elems, n, 0)[1] * 4, n_chunks=chunks)
             ms = timeit(lambda: sess.call(x, y, "scale", 2.0), devs, iters)
@@ -69,15 +69,20 @@ def main():
             emit(what="c2_device", n_gpus=n, mib=mib, mode="push_push_pipeline", chunks=chunks, ms=ms,
                  gbps=2 * elems * 4 / ms / 1e6, link_gbps_per_dir=(n - 1) / n * elems * 4 / ms / 1e6, ok=ok)
             del sess
-        if mib == 256:
-            for cps in (4, 8):
-                ops.set_tuning(21, cps)
-                sess = ops.PushSession(devs, ops.shard_bounds(elems, n, 0)[1] * 4, n_chunks=32)
-                ms = timeit(lambda: sess.call(x, y, "scale", 2.0), devs, iters)
-                emit(what="c2_device", n_gpus=n, mib=mib, mode="push_push_pipeline", chunks=32, scatter_ctas_per_sm=cps, ms=ms,
-                     gbps=2 * elems * 4 / ms / 1e6, link_gbps_per_dir=(n - 1) / n * elems * 4 / ms / 1e6)
-                del sess
-            ops.set_tuning(21, 8)
+        if mib in (256, 1024):
+            for slice_ in (1, 2, 4, 8, 16):
+                for cps in (0, 4):
+                    ops.set_tuning(23, slice_)
+                    ops.set_tuning(21, cps)
+                    sess = ops.PushSession(devs, ops.shard_bounds(elems, n, 0)[1] * 4, n_chunks=32)
+                    ms = timeit(lambda: sess.call(x, y, "scale", 2.0), devs, iters)
+                    ok = bool(torch.equal(y[-4096:], x[-4096:] * 2))
+                    emit(what="c2_device", n_gpus=n, mib=mib, mode="push_push_pipeline", chunks=32, slice=slice_,
+                         scatter_ctas_per_sm=cps, ms=ms, gbps=2 * elems * 4 / ms / 1e6,
+                         link_gbps_per_dir=(n - 1) / n * elems * 4 / ms / 1e6, ok=ok)
+                    del sess
+            ops.set_tuning(23, 4)
+            ops.set_tuning(21, 0)
         del x, y
 
 
