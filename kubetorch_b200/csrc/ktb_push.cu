@@ -59,9 +59,8 @@ __global__ void __launch_bounds__(kPushThreads)
   const uint32_t total_tiles = tiles_per_chunk * (uint32_t)a.n_chunks;
   __shared__ bool last;
   // Every CTA streams a SLICE of `slice` consecutive 16 KiB tiles (chunk-major tile order) and reports them with ONE
-  // system fence + one atomic: the fence has to wait for the acknowledgement of every peer store the CTA has in flight,
-  // and under a saturated link that wait is queueing delay (ncu: the per-tile-fence form moved 134 MB in 0.42 ms where
-  // the plain push kernel needs 0.31 ms).  grid = ceil(tiles / slice) by default; a smaller grid walks further slices.
+  // system fence + one atomic.  slice = 1 measured best (see g_push_slice); grid = ceil(tiles / slice) by default, a
+  // smaller grid walks further slices.
   uint32_t cur_chunk = 0xffffffffu, n_done = 0;
   auto flush = [&]() {   // all threads call it together
     __syncthreads();     // every thread's stores of the finished tiles are issued
@@ -225,8 +224,10 @@ size_t ktb_push_control_bytes(void) { return 4096; }
 // grid cap of the scatter in CTAs per SM (0 = no cap: ceil(tiles / slice) CTAs).  Caps were measured slower for the
 // element-wise call (profiles/r2_summary.md §2); ktb_push_scatter_chunked takes its own cap for the MLP.
 std::atomic<int> g_push_scatter_ctas_per_sm{0};   // ktb_set_tuning(21, n)
-// tiles (16 KiB) per CTA per system fence, both sides
-std::atomic<int> g_push_slice{4};                 // ktb_set_tuning(23, n)
+// tiles (16 KiB) per CTA per system fence, both sides.  Measured (profiles/r2f_push_sweep_2gpu.jsonl): 1 is best —
+// 256 MiB at N=2: slice 1 0.317 ms, 2 0.377, 4 0.409, 8-16 0.413; many short-lived CTAs keep more stores in flight
+// than fewer CTAs streaming longer slices, and the per-CTA fence is not what limits them
+std::atomic<int> g_push_slice{1};                 // ktb_set_tuning(23, n)
 
 // chunk_elems == 0: n_chunks pieces per shard (chunk_bounds); otherwise pieces of exactly chunk_elems elements
 // (the consumer of ktb_mlp_bf16_pushed wants whole GEMM row chunks), n_chunks = ceil(largest shard / chunk_elems).

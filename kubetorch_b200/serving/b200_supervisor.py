@@ -455,8 +455,11 @@ class B200Supervisor:
         """A timed-out in-kernel wait (a rank's GPU stalled or died) surfaces as the reference's
         PodTerminatedError (kt/serving/utils.py:111-190), not as silently stale results: the consume kernel skips
         its stores on a timeout, the status word is mirrored to the host behind every call."""
+        import datetime
+
         raise PodTerminatedError(pod_name=f"{self.name}-0", reason="DeviceTimeout", status_code=503,
-                                 events=[{"reason": "DeviceTimeout", "message": str(e)}]) from None
+                                 events=[{"timestamp": datetime.datetime.now(datetime.timezone.utc).isoformat(),
+                                          "reason": "DeviceTimeout", "message": str(e)}]) from None
 
     def check_device_health(self):
         """Synchronous form (reads every control block): used at teardown and by tests."""

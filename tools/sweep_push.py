@@ -81,7 +81,7 @@ def main():
                          scatter_ctas_per_sm=cps, ms=ms, gbps=2 * elems * 4 / ms / 1e6,
                          link_gbps_per_dir=(n - 1) / n * elems * 4 / ms / 1e6, ok=ok)
                     del sess
-            ops.set_tuning(23, 4)
+            ops.set_tuning(23, 1)
             ops.set_tuning(21, 0)
         del x, y
 
