@@ -382,13 +382,18 @@ def run_ours(args):
                 L.call("ktb_map", dev, op, dt, x_ptr + off + bb * gran * e_, y_ptr + off + bb * gran * e_,
                        (ee - bb) * gran, float(a), float(b), L.VARIANT_AUTO, stream)
 
-        def call_push(n, gran, dt, op, a, b, off):
+        lanes = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)] if rank == 0 else None
+
+        def call_push(n, gran, dt, op, a, b, off, lane=None):
+            """lane = None: on the current stream; 0/1: rank 0 issues on one of two alternating streams, so that the
+            scatter of call k+1 overlaps the gather of call k (two calls in flight; staging and counters are per parity)."""
             seq_box[0] += 1
             seq = seq_box[0]
             e_ = esize[dt]
             bb, ee = ops.shard_bounds(n // gran, world, rank)
             if rank == 0:
-                cur = torch.cuda.current_stream(dev)
+                cur = torch.cuda.current_stream(dev) if lane is None else lanes[lane]
+                st_ = cur.cuda_stream
                 if ee > bb:   # the root's own shard maps on a side stream, forked and launched before the scatter
                     ev_fork.record(cur)
                     side.wait_event(ev_fork)
@@ -396,8 +401,8 @@ def run_ours(args):
                            (ee - bb) * gran, float(a), float(b), L.VARIANT_AUTO, side.cuda_stream)
                     ev_join.record(side)
                 L.call("ktb_push_scatter", dev, x_ptr + off, n, gran, dt, world, 0, c_stage, stride, c_ctrl,
-                       ctrl_root_ptr, n_chunks, seq, stream)
-                L.call("ktb_push_wait", dev, ctrl_root_ptr, world, 0, seq, stream)
+                       ctrl_root_ptr, n_chunks, seq, st_)
+                L.call("ktb_push_wait", dev, ctrl_root_ptr, world, 0, seq, st_)
                 if ee > bb:
                     cur.wait_event(ev_join)
             else:
@@ -475,6 +480,31 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
 
+    def time_two_in_flight():
+        """The push pipeline with TWO calls in flight (rank 0 alternates two streams): throughput of a caller that
+        keeps the port busy both ways all the time.  Reported beside `value`, never as `value`."""
+        for i in range(W + (W & 1)):
+            call_push(*TIMED, lane=i & 1)
+        sync_all()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        if rank == 0:
+            for ln in lanes:
+                ln.wait_event(ev0)
+        for i in range(K):
+            call_push(*TIMED, lane=i & 1)
+        if rank == 0:
+            for ln in lanes:
+                e = torch.cuda.Event()
+                e.record(ln)
+                torch.cuda.current_stream(dev).wait_event(e)
+        ev1.record()
+        sync_all()
+        ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([ms], device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / K
+
     sampler = ClockSampler(dev)
     if rank == 0:
         sampler.start()
@@ -487,6 +517,17 @@ def run_ours(args):
         ms_push, t0b, t_wall1 = time_mode(call_push)
         check_result("push")
         modes["push_push_flag_pipeline"] = ms_push
+    two_in_flight = None
+    if world > 1:
+        try:
+            ms2 = time_two_in_flight()
+            check_result("push, two calls in flight")
+            two_in_flight = {"ms_per_step": ms2, "arg_plus_result_gbps": 2 * nbytes / (ms2 * 1e-3) / 1e9,
+                             "root_port_gbps_per_direction": (n_gpus - 1) / n_gpus * nbytes / (ms2 * 1e-3) / 1e9,
+                             "what": "push/push pipeline, rank 0 alternates two streams: call k+1's scatter overlaps call k's "
+                                     "gather (not used for `value`)"}
+        except Exception as e:  # noqa: BLE001
+            two_in_flight = {"error": f"{type(e).__name__}: {e}"[:300]}
     # The timed region lasts a few milliseconds — shorter than one nvidia-smi sample — so the clocks are sampled over
     # an extended loop of the SAME call right after it (~0.6 s under load, all ranks take part).
     best_mode = min(modes, key=modes.get)
@@ -695,6 +736,16 @@ def run_ours(args):
                     torch.cuda.synchronize()
                     return a.elapsed_time(b2) / iters
 
+                # the same 2048 small calls through the PUBLIC API in one go: remote.map(xs) -> one segmented launch
+                for _ in range(3):
+                    outs = r_dbl.map(xs, serialization="pickle")
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(10):
+                    outs = r_dbl.map(xs, serialization="pickle")
+                torch.cuda.synchronize()
+                small_["public_api_map_calls_per_sec"] = 10 * len(xs) / (time.perf_counter() - t0)
+                assert len(outs) == len(xs) and torch.equal(torch.cat(outs[5]), xs[5] * 2)
                 small_["one_launch_per_call_calls_per_sec"] = 1e3 / dev_ms(
                     lambda: ops.map_tensor(xs[0], "scale", 2.0, out=ys[0]), 2000)
                 small_["coalesced_batch_calls_per_sec"] = 2048 * 1e3 / dev_ms(plan.run, 20)
@@ -813,7 +864,7 @@ def run_ours(args):
                 "residency": "args/results resident on GPU 0",
                 "mode": "single controller" if world == 1 else "one process per GPU, CUDA-IPC peer arenas, calls "
                         "pipelined per rank",
-                "transfer": best_mode, "ms_per_step_by_transfer": modes,
+                "transfer": best_mode, "ms_per_step_by_transfer": modes, "two_calls_in_flight": two_in_flight,
                 "l2": "inputs+outputs (512 MiB) exceed the 126 MB L2; no flush needed",
             },
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "parity": parity,

@@ -365,7 +365,7 @@ __device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsig
 //   [ 512, 1024)  ack[r]    (u64 per rank, written by rank r into the ROOT's block)
 //   [1024, 1028)  ticket    (u32, local)
 //   [1032, 1036)  status    (u32, local; nonzero = a spin timed out)
-//   [2048, 2304)  chunk_done[c]  (u32 per chunk, root-local: finished tiles of chunk c in the running call)
+//   [2048, 2560)  chunk_done[seq & 1][c]  (u32 per chunk and call parity, root-local: finished tiles of chunk c)
 #define KTB_CTRL_READY 0
 #define KTB_CTRL_ACK 512
 #define KTB_CTRL_TICKET 1024

@@ -252,7 +252,9 @@ static int push_scatter_impl(const char* who, int root_dev, const void* src_root
   KTB_GUARD(root_dev);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* croot = static_cast<uint8_t*>(ctrl_root);
-  unsigned int* chunk_done = reinterpret_cast<unsigned int*>(croot + KTB_CTRL_CHUNK_DONE);
+  // per call parity: the scatters of two consecutive calls may overlap when the caller alternates streams
+  unsigned int* chunk_done =
+      reinterpret_cast<unsigned int*>(croot + KTB_CTRL_CHUNK_DONE) + (size_t)(seq & 1) * KTB_PUSH_MAX_CHUNKS;
   unsigned int* status = reinterpret_cast<unsigned int*>(croot + KTB_CTRL_STATUS);
   const size_t buf_off = (size_t)(seq & 1) * stage_stride;
   PushScatterArgs a;

@@ -183,6 +183,37 @@ def fast_map(device: int, op: str, alpha: float, beta: float):
     return launch
 
 
+def batch_map(device: int, op: str, alpha: float, beta: float):
+    """run(dtype_code, dtype, xs, sizes) -> tuple of outputs: n small calls out_i = op(x_i) in ONE segmented launch
+    (ktb_map_batch), the outputs carved out of one fresh arena (256-byte aligned, so every output is a valid vector
+    target)."""
+    ensure_init({device})
+    fn = L.load().ktb_map_batch
+    op_code, dev = OPS[op], int(device)
+    raw = _raw_stream if _raw_stream is not None else (lambda d: torch.cuda.current_stream(d).cuda_stream)
+
+    def run(code, dtype, xs, sizes):
+        n = len(xs)
+        es = xs[0].element_size()
+        align = 256 // es
+        padded = [(s + align - 1) // align * align for s in sizes]
+        arena = torch.empty(sum(padded), dtype=dtype, device=f"cuda:{dev}")
+        base = arena.data_ptr()
+        outs, dst, off = [], [], 0
+        pieces = arena.split(padded)
+        for i in range(n):
+            outs.append(pieces[i][:sizes[i]] if padded[i] != sizes[i] else pieces[i])
+            dst.append(base + off * es)
+            off += padded[i]
+        rc = fn(dev, op_code, code, (ctypes.c_void_p * n)(*[x.data_ptr() for x in xs]), (ctypes.c_void_p * n)(*dst),
+                (ctypes.c_size_t * n)(*sizes), n, alpha, beta, raw(dev))
+        if rc:
+            L.check(rc)
+        return outs
+
+    return run
+
+
 _ws_cache = {}
 
 

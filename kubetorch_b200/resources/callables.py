@@ -82,6 +82,7 @@ class Module:
         self._http_client = None
         self._supervisor = None
         self._fast = None
+        self._batch = None
         self._fast_sers = frozenset()
         self._serialization = "json"
         self._async = False
@@ -236,6 +237,7 @@ class Module:
             allowed = compute.allowed_serialization_str.split(",")
             self._fast_sers = frozenset(s for s in ("pickle", "none") if s in allowed)
             self._fast = sup.fast_path(bool(self._fast_sers))
+            self._batch = sup.batch_path(bool(self._fast_sers)) if hasattr(sup, "batch_path") else None
         _DEPLOYED[self.service_name] = self
         return self
 
@@ -258,7 +260,7 @@ class Module:
             self._supervisor.cleanup()
             self._supervisor = None
         self._http_client = None
-        self._fast = None
+        self._fast = self._batch = None
         _DEPLOYED.pop(self.service_name, None)
 
     def _client(self, *args, **kwargs):
@@ -313,6 +315,19 @@ class Fn(Module):
         return await client.call_method_async(self.endpoint(), stream_logs, self.logging_config,
                                               stream_metrics=stream_metrics, headers=self.request_headers, body=body,
                                               serialization=serialization)
+
+    def map(self, inputs, **kwargs):
+        """`[remote(x, **kwargs) for x in inputs]` — the results are exactly those — but a run of small device-resident
+        tensors for a @kt.mapped element-wise function is coalesced into ONE segmented kernel launch (not in the
+        reference's API: its remote-map is one HTTP call per item)."""
+        inputs = list(inputs)
+        batch = self._batch
+        ser = kwargs.get("serialization", self._serialization)
+        if batch is not None and not self._async and ser in self._fast_sers and set(kwargs) <= {"serialization"}:
+            out = batch(inputs)
+            if out is not None:
+                return out
+        return [self(x, **kwargs) for x in inputs]
 
 
 def fn(function_obj=None, name: str = None, get_if_exists=True, reload_prefixes=None, sync_dir=None, remote_dir=None,

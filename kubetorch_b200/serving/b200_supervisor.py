@@ -312,6 +312,57 @@ class B200Supervisor:
 
         return fast
 
+    def batch_path(self, serialization_ok):
+        """`batch(xs) -> [result per x] | None`: MANY small calls of the deployed function coalesced into ONE segmented
+        launch (ktb_map_batch: the descriptors ride in the kernel parameters), results carved out of one arena.
+        Reached from the public API as `remote.map(xs)`.  Same coverage rules as fast_path(); None = not covered."""
+        import inspect
+
+        import torch
+
+        method = self._callable
+        if not (inspect.isfunction(method) or inspect.ismethod(method)) or not serialization_ok or self.ops is None:
+            return None
+        spec = mapped_spec(method)
+        if spec is None or spec.op not in ELEMENTWISE_OPS or spec.reduce is not None or not hasattr(self.ops, "batch_map"):
+            return None
+        if not (isinstance(spec.alpha, (int, float)) and isinstance(spec.beta, (int, float))):
+            return None
+        if len(inspect.signature(method).parameters) != 1 or (self.placement == "ranks" and self.world_size > 1):
+            return None
+        integral = float(spec.alpha).is_integer() and float(spec.beta).is_integer()
+        world, root, distributed = self.world_size, self.devices[0], self.distributed
+        codes = self.ops.fast_dtype_codes(integral)
+        run = self.ops.batch_map(root, spec.op, float(spec.alpha), float(spec.beta))
+        small = self.SMALL_CALL_BYTES
+        Tensor = torch.Tensor
+
+        def batch(xs):
+            if not xs:
+                return []
+            dt = xs[0].dtype if type(xs[0]) is Tensor else None
+            code = codes.get(dt)
+            if code is None:
+                return None
+            es = xs[0].element_size()
+            for x in xs:
+                if type(x) is not Tensor or x.dtype is not dt or not x.is_cuda or x.device.index != root or \
+                        x.dim() != 1 or not x.is_contiguous() or x.numel() == 0 or x.numel() * es >= small:
+                    return None
+            sizes = [x.numel() for x in xs]
+            outs = run(code, dt, xs, sizes)
+            if world == 1:
+                return [[o] for o in outs] if distributed else list(outs)
+            res = []
+            for o in outs:
+                v = list(o.chunk(world))
+                while len(v) < world:
+                    v.append(o[:0])
+                res.append(v)
+            return res
+
+        return batch
+
     # ---- the call ---------------------------------------------------------------------------------------
     def call(self, request, cls_or_fn_name, method_name=None, params=None, distributed_subcall=False):
         serialization = request.headers.get("X-Serialization", "json")

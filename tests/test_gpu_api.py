@@ -669,3 +669,27 @@ def test_device_stall_maps_to_pod_terminated_error():
         assert ei.value.reason == "DeviceTimeout" and ei.value.status_code == 503
     finally:
         remote.teardown()
+
+
+def test_map_coalesces_small_calls_and_equals_a_loop_of_calls(golden):
+    """remote.map(xs) == [remote(x) for x in xs] — one segmented launch for the covered case, a plain loop otherwise."""
+    double = _mapped(cases.double, "scale", alpha=2.0)
+    for world in (1, 3):
+        r = _deploy(double, world, f"t-map-{world}", placement="auto")
+        try:
+            assert r._batch is not None
+            gen = torch.Generator().manual_seed(7)
+            xs = [torch.randn(n, generator=gen).cuda() for n in (1, 3, 255, 256, 257, 1003, 4099)] * 40
+            got = r.map(xs, serialization="pickle")
+            want = [r(x, serialization="pickle") for x in xs]
+            assert len(got) == len(want) == len(xs)
+            for g, w, x in zip(got, want, xs):
+                assert len(g) == len(w) == world
+                assert all(a.dtype == b.dtype and tuple(a.shape) == tuple(b.shape) and torch.equal(a, b) for a, b in zip(g, w))
+                assert torch.equal(torch.cat(g).cpu(), x.cpu() * 2)
+            mixed = [torch.randn(5), torch.randn(7).cuda()]              # a host tensor in the list: plain loop, same results
+            out = r.map(mixed, serialization="pickle")
+            assert torch.equal(torch.cat(out[0]), mixed[0] * 2) and torch.equal(torch.cat(out[1]).cpu(), mixed[1].cpu() * 2)
+            assert r.map([], serialization="pickle") == []
+        finally:
+            r.teardown()
