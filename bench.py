@@ -575,12 +575,15 @@ def run_ours(args):
         roof = {"bound": "nvlink", "achieved": achieved, "peak": 770.0, "unit": "GB/s", "frac": achieved / 770.0,
                 "traffic": traffic.get("bytes"), "traffic_source": traffic.get("source"),
                 "peak_source": "measured peer copy per direction (B200_PROFILING.md)",
-                "kernel": "ktb::map_vec_kernel<F32,SCALE,32B> on peer pointers",
+                "kernel": ("ktb::map_vec_kernel<F32,SCALE,32B> on peer pointers" if best_mode == "pull_push_fused_kernel"
+                           else "ktb::push_scatter_kernel (root) + ktb::push_consume_kernel<F32,SCALE> (ranks)"),
                 "algorithmic_bytes_per_launch": 2 * shard_bytes,
-                "note": "bytes crossing the root GPU's NVLink port per direction per call / step time; both "
-                        "directions are busy at once, where the copy engines reach 353 GB/s per direction on this pool "
-                        "(profiles/r1f_sweep_peer_2gpu.jsonl: torch_peer_copy_duplex)",
-                "duplex_copy_engine_reference": 353.4, "frac_of_duplex_reference": achieved / 353.4}
+                "note": "bytes crossing the root GPU's NVLink port per direction per call / step time, both directions busy "
+                        "at once. Measured ceiling of this duplex pattern with INDEPENDENT streams (no scatter->gather "
+                        "dependency): 689 GB/s per direction at N=2, 618 at N=8 (profiles/r2_summary.md §1); one GPU "
+                        "driving both directions caps at 489",
+                "duplex_ceiling_gbps": 689.0 if n_gpus == 2 else 618.0,
+                "frac_of_duplex_ceiling": achieved / (689.0 if n_gpus == 2 else 618.0)}
 
     # everything below runs on rank 0 as ONE controller process driving all N GPUs through the public API (the product's
     # launch mode); the other torchrun ranks release their arenas and wait on a CPU barrier
@@ -959,18 +962,21 @@ def _traffic(n_gpus: int) -> dict:
     try:
         with open(os.path.join(REPO, "profiles", "roofline_traffic.json")) as f:
             rec = json.load(f)
-        h = hashlib.sha256()
-        for name in ("ktb_map.cu", "ktb_common.cuh"):
-            with open(os.path.join(REPO, "kubetorch_b200", "csrc", name), "rb") as fh:
-                h.update(fh.read())
-        if rec.get("kernel_source_sha256") != h.hexdigest():
+        from kubetorch_b200.device import lib as _L
+
+        if rec.get("kernel_source_sha256") != _L.map_kernel_source_sha256():
             return {"bytes": None, "source": "stale: kernel source changed since the ncu capture in profiles/roofline_traffic.json"}
-        key = "dram_bytes_per_launch" if n_gpus == 1 else f"nvlink_bytes_per_launch_n{n_gpus}"
-        val = rec.get(key)
-        if val is None and n_gpus > 1:
-            val = rec.get("nvlink_bytes_per_launch_n2")
-            return {"bytes": None if val is None else val, "source": rec.get("source", "") + " (N=2 capture)"}
-        return {"bytes": val, "source": rec.get("source")}
+        if n_gpus == 1:
+            return {"bytes": rec.get("dram_bytes_per_launch"), "source": rec.get("source")}
+        nv = rec.get("nvlink") or {}
+        if not nv:
+            return {"bytes": None, "source": "no NVLink capture"}
+        # bytes on the wire through the root's port per call, both directions: user bytes x the measured wire/user ratio
+        # of the push kernels (N=2 capture; the ratio is a property of the 128-byte write packets, not of N)
+        shard = -(-N_ELEMS // n_gpus) * 4
+        user = (n_gpus - 1) * shard
+        return {"bytes": int(2 * user * nv["wire_per_user"]),
+                "source": nv["source"] + f"; scaled to N={n_gpus}: 2 directions x {user} user bytes x {nv['wire_per_user']:.4f}"}
     except Exception as e:  # noqa: BLE001
         return {"bytes": None, "source": f"unavailable: {type(e).__name__}"}
 

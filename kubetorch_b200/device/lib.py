@@ -105,6 +105,25 @@ def lib_path() -> str:
     return _LIB_PATH
 
 
+def map_kernel_source_sha256() -> str:
+    """sha256 of the SOURCE of the dominant kernel (the "VEC" section of csrc/ktb_map.cu = map_vec_kernel and its
+    load/store helpers, plus the per-element op math and the streaming PTX helpers of ktb_common.cuh).  Stamped into
+    profiles/roofline_traffic.json at ncu-capture time; bench.py reports `traffic: null` ("stale") when it differs."""
+    import hashlib
+
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
+
+    def section(name, start, stop):
+        text = open(os.path.join(csrc, name)).read()
+        a = text.index(start)
+        return text[a:text.index(stop, a)]
+
+    h = hashlib.sha256()
+    h.update(section("ktb_map.cu", "// ---- VEC ---", "// ---- SCALAR ---").encode())
+    h.update(section("ktb_common.cuh", "// ---- per-element op math", "// ---- PTX: mbarrier").encode())
+    return h.hexdigest()
+
+
 def load() -> ctypes.CDLL:
     """Load libktb200.so (once) and declare every prototype. Raises KtbLibraryMissing if absent."""
     global _lib

@@ -4,7 +4,7 @@
     ncu -i gpurun_out/r2_map_vec.ncu-rep --page raw --csv > profiles/r2_map_vec_ncu_raw.csv
     python tools/update_traffic.py profiles/r2_map_vec_ncu_raw.csv [nvlink.csv ...]
 
-Stamps the sha256 of the kernel's SOURCE (ktb_map.cu + ktb_common.cuh): bench.py reports `traffic: null` with a
+Stamps the sha256 of the kernel's SOURCE (kubetorch_b200.device.lib.map_kernel_source_sha256): bench.py reports `traffic: null` with a
 "stale" note when the source has changed since the capture, instead of quoting bytes of a kernel that no longer exists."""
 import csv
 import hashlib
@@ -16,11 +16,10 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def source_sha():
-    h = hashlib.sha256()
-    for name in ("ktb_map.cu", "ktb_common.cuh"):
-        with open(os.path.join(REPO, "kubetorch_b200", "csrc", name), "rb") as f:
-            h.update(f.read())
-    return h.hexdigest()
+    sys.path.insert(0, REPO)
+    from kubetorch_b200.device import lib as L
+
+    return L.map_kernel_source_sha256()
 
 
 def raw_rows(path):
