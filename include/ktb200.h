@@ -211,7 +211,9 @@ int ktb_push_scatter(int root_dev, const void* src_root, size_t n_elems, size_t 
                      uintptr_t stream);
 /* The same root side with pieces of EXACTLY chunk_elems elements per rank (n_chunks = ceil(largest shard /
  * chunk_elems) <= 64): for consumers that need whole work units per piece (ktb_mlp_bf16_pushed: GEMM row chunks).
- * ctas_per_sm caps the persistent grid (0 = library default) so the root's own compute keeps its share of every SM. */
+ * ctas_per_sm caps the persistent grid (0 = library default) so the root's own compute keeps its share of every SM.
+ * A rank whose stage_peer[r] is NULL is skipped (also in ktb_push_scatter / ktb_push_scatter_ce): two calls with
+ * complementary NULL masks split the ranks between engines (hybrid copy-engine + SM scatter). */
 int ktb_push_scatter_chunked(int root_dev, const void* src_root, size_t n_elems, size_t granule, int dtype,
                              int n_ranks, int root_rank, void* const* stage_peer, size_t stage_stride,
                              void* const* ctrl_peer, void* ctrl_root, size_t chunk_elems, int ctas_per_sm,

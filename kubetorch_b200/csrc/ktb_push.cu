@@ -273,7 +273,8 @@ static int push_scatter_impl(const char* who, int root_dev, const void* src_root
       chunk_bounds(se - sb, n_chunks, 1, &per, &dummy);   // start of chunk 1 = elements per chunk
       if (per == 0) per = c0e - c0b;                      // single-chunk (or empty) shard
     }
-    KTB_REQUIRE(stage_peer[r] && ctrl_peer[r], KTB_ERR_ARG, "%s: rank %d has no staging/control block", who, r);
+    if (!stage_peer[r]) continue;   // not served by this call (a hybrid scatter splits the ranks between two engines)
+    KTB_REQUIRE(ctrl_peer[r], KTB_ERR_ARG, "%s: rank %d has no control block", who, r);
     KTB_REQUIRE((se - sb) * es <= stage_stride, KTB_ERR_ARG, "%s: shard of rank %d exceeds stage_stride", who, r);
     const int i = a.n++;
     a.src[i] = static_cast<const uint8_t*>(src_root) + sb * es;
@@ -366,8 +367,8 @@ int ktb_push_scatter_ce(int root_dev, const void* src_root, size_t n_elems, size
     ktb_shard_bounds(n_elems / granule, n_ranks, r, &b, &e);
     sb[r] = b * granule;
     sl[r] = (e - b) * granule;
-    if (r == root_rank) continue;
-    KTB_REQUIRE(stage_peer[r] && ctrl_peer[r], KTB_ERR_ARG, "ktb_push_scatter_ce: rank %d has no staging/control block", r);
+    if (r == root_rank || !stage_peer[r]) continue;   // null staging = rank served by another scatter call
+    KTB_REQUIRE(ctrl_peer[r], KTB_ERR_ARG, "ktb_push_scatter_ce: rank %d has no control block", r);
     KTB_REQUIRE(sl[r] * es <= stage_stride, KTB_ERR_ARG, "ktb_push_scatter_ce: shard of rank %d exceeds stage_stride", r);
     if (!ce_stream[root_dev][r]) {
       KTB_CK(cudaStreamCreateWithFlags(&ce_stream[root_dev][r], cudaStreamNonBlocking));
@@ -382,7 +383,7 @@ int ktb_push_scatter_ce(int root_dev, const void* src_root, size_t n_elems, size
   }
   for (size_t c = 0; c < n_chunks; ++c) {
     for (int r = 0; r < n_ranks; ++r) {
-      if (r == root_rank) continue;
+      if (r == root_rank || !stage_peer[r]) continue;
       cudaStream_t cs = ce_stream[root_dev][r];
       const size_t lo = std::min(sl[r], c * chunk_elems), hi = std::min(sl[r], lo + chunk_elems);
       if (hi > lo)
@@ -395,7 +396,7 @@ int ktb_push_scatter_ce(int root_dev, const void* src_root, size_t n_elems, size
     }
   }
   for (int r = 0; r < n_ranks; ++r) {   // the caller's stream "contains" the scatter (src may be reused after it)
-    if (r == root_rank) continue;
+    if (r == root_rank || !stage_peer[r]) continue;
     KTB_CK(cudaEventRecord(ce_done[root_dev][r], ce_stream[root_dev][r]));
     KTB_CK(cudaStreamWaitEvent(st, ce_done[root_dev][r], 0));
   }

@@ -84,7 +84,11 @@ def _weights_on(dev: int, ws: Sequence[torch.Tensor]) -> List[torch.Tensor]:
     return out
 
 
-SCATTER_ENGINE = "ce"        # "ce": copy engines push the observation chunks; "sm": the persistent scatter kernel
+SCATTER_ENGINE = "ce"        # "ce": copy engines push the observation chunks; "sm": the capped scatter kernel;
+                             # "hybrid": copy engines serve the first CE_RANKS ranks, the capped scatter kernel the rest
+                             # (the root's copy engines alone reach ~434 GB/s of egress, a 2-CTA/SM scatter ~407: together
+                             # they approach the port's ~640)
+CE_RANKS = 3
 SCATTER_CTAS_PER_SM = 2
 PUSH_CHUNK_ROWS = 37888      # two waves of 74 CTA pairs x 256 rows: whole waves for the fused layer-2+head kernel
 _push_states = {}
@@ -104,7 +108,9 @@ class _MlpPushState:
         self.stage_ptrs = L.arr(ctypes.c_void_p, [0 if t is None else t.data_ptr() for t in self.stage])
         self.ctrl_ptrs = L.arr(ctypes.c_void_p, [c.data_ptr() for c in self.ctrl])
         self.side = torch.cuda.Stream(devs[0])
+        self.scatter = torch.cuda.Stream(devs[0])      # the SM scatter kernel of a hybrid scatter
         self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
+        self.ev_scatter = torch.cuda.Event()
         self.status_host = torch.zeros(len(devs), dtype=torch.int32).pin_memory()
         self.status_dev = [c[1032:1036].view(torch.int32) for c in self.ctrl]
 
@@ -140,14 +146,21 @@ def _mlp_scatter_gather_pushed(obs_root, w1, w2, w3, devs, out_root, bounds, wei
             ws = weights[root]
             mlp_forward(obs_root[b0:e0], ws[0], ws[1], ws[2], out=out_root[b0:e0], device=root, stream=st.side, staged=False)
         st.ev_join.record(st.side)
-        if SCATTER_ENGINE == "ce":   # copy engines move the rows: the root's SMs stay with its own GEMMs
-            L.call("ktb_push_scatter_ce", root, obs_root.data_ptr(), obs_root.numel(), d_in, L.BF16, n, 0,
-                   L.arr(ctypes.c_int, list(devs)), st.stage_ptrs, st.stride, st.ctrl_ptrs, st.ctrl[0].data_ptr(),
-                   PUSH_CHUNK_ROWS * d_in, seq, int(root_stream.cuda_stream))
-        else:
-            L.call("ktb_push_scatter_chunked", root, obs_root.data_ptr(), obs_root.numel(), d_in, L.BF16, n, 0, st.stage_ptrs,
+        engine = SCATTER_ENGINE if n > 2 or SCATTER_ENGINE != "hybrid" else "ce"
+        ptrs = [0 if t is None else t.data_ptr() for t in st.stage]
+        n_ce = n - 1 if engine == "ce" else (0 if engine == "sm" else min(CE_RANKS, n - 2))
+        ce_ptrs = L.arr(ctypes.c_void_p, [p if 1 <= r <= n_ce else 0 for r, p in enumerate(ptrs)])
+        sm_ptrs = L.arr(ctypes.c_void_p, [p if r > n_ce else 0 for r, p in enumerate(ptrs)])
+        if n_ce < n - 1:             # the capped scatter kernel first: its few CTAs per SM leave room for the root's GEMMs
+            st.scatter.wait_event(st.ev_fork)
+            L.call("ktb_push_scatter_chunked", root, obs_root.data_ptr(), obs_root.numel(), d_in, L.BF16, n, 0, sm_ptrs,
                    st.stride, st.ctrl_ptrs, st.ctrl[0].data_ptr(), PUSH_CHUNK_ROWS * d_in, SCATTER_CTAS_PER_SM, seq,
-                   int(root_stream.cuda_stream))
+                   int(st.scatter.cuda_stream))
+            st.ev_scatter.record(st.scatter)
+        if n_ce > 0:                 # copy engines move the rows of the other ranks: no SM of the root involved
+            L.call("ktb_push_scatter_ce", root, obs_root.data_ptr(), obs_root.numel(), d_in, L.BF16, n, 0,
+                   L.arr(ctypes.c_int, list(devs)), ce_ptrs, st.stride, st.ctrl_ptrs, st.ctrl[0].data_ptr(),
+                   PUSH_CHUNK_ROWS * d_in, seq, int(root_stream.cuda_stream))
     streams = {d: torch.cuda.current_stream(d) for d in devs[1:]}
     scratch = {d: _scratch_for(d, max(e - b for b, e in bounds), d_hidden) for d in devs[1:]}
 
@@ -168,6 +181,8 @@ def _mlp_scatter_gather_pushed(obs_root, w1, w2, w3, devs, out_root, bounds, wei
     with torch.cuda.device(root):
         L.call("ktb_push_wait", root, st.ctrl[0].data_ptr(), n, 0, seq, int(root_stream.cuda_stream))
         root_stream.wait_event(st.ev_join)
+        if n_ce < n - 1:
+            root_stream.wait_event(st.ev_scatter)
     for r, d in enumerate(devs):   # stream-ordered mirror of the sticky status words (seen at the next call)
         with torch.cuda.device(d):
             st.status_host[r:r + 1].copy_(st.status_dev[r], non_blocking=True)

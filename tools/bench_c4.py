@@ -25,10 +25,12 @@ from oracle import cases  # noqa: E402
 def main():
     n_gpus = int(sys.argv[1]) if len(sys.argv) > 1 else torch.cuda.device_count()
     transfer = sys.argv[2] if len(sys.argv) > 2 else "auto"          # auto | pull | push
-    if len(sys.argv) > 3:                                              # ce | sm (engine of the pushed scatter)
+    if len(sys.argv) > 3:                                              # ce | sm | hybrid (engine of the pushed scatter)
         from kubetorch_b200.device import mlp as _mlp
 
         _mlp.SCATTER_ENGINE = sys.argv[3]
+        if len(sys.argv) > 4:
+            _mlp.CE_RANKS = int(sys.argv[4])
     shards, rows = 4096, 512
     M = shards * rows
     g = torch.Generator(device="cuda:0").manual_seed(0)
