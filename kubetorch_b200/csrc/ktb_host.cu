@@ -286,6 +286,8 @@ int ktb_host_alloc_sharded(size_t nbytes, int n_parts, const size_t* part_end, c
     if (rc) return rc;
     prev = part_end[i];
   }
+  // the issue threads carry one job at a time (single-slot mailboxes): allocations and host-path calls take turns
+  std::lock_guard<std::mutex> lk(g_host_call_mu);
   constexpr size_t kHuge = 2u << 20;
   const size_t len = (nbytes + kHuge - 1) / kHuge * kHuge + kHuge;
   void* base = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);

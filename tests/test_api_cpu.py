@@ -482,3 +482,60 @@ def test_concurrent_large_payloads_do_not_interleave_on_the_rank_pipes():
             assert len(out[i]) == 2 and all(torch.equal(o, xs[i]) for o in out[i])
     finally:
         remote.teardown()
+
+
+def test_partial_deployments_spread_over_numa_nodes():
+    """B200Supervisor._pick_devices: N of the visible GPUs, GPU 0 first, spread over the sockets when N < visible."""
+    from kubetorch_b200.serving.b200_supervisor import B200Supervisor
+
+    class Box:
+        def __init__(self, nodes):
+            self.nodes = nodes
+
+        def device_count(self):
+            return len(self.nodes)
+
+        def device_numa_node(self, d):
+            return self.nodes[d]
+
+    sup = B200Supervisor()
+    sup.ops = Box([0, 0, 0, 0, 1, 1, 1, 1])
+    assert [sup._pick_devices(n) for n in (1, 2, 3, 4, 6, 8)] == \
+        [[0], [0, 4], [0, 1, 4], [0, 1, 4, 5], [0, 1, 2, 4, 5, 6], list(range(8))]
+    sup.ops = Box([1, 1, 1, 1, 0, 0, 0, 0])                # node numbering is arbitrary: GPU 0's socket comes first
+    assert sup._pick_devices(4) == [0, 1, 4, 5]
+    sup.ops = Box([0, 0, 0, 0])                            # one socket: first N
+    assert sup._pick_devices(2) == [0, 1]
+    sup.ops = Box([-1] * 8)                                # no topology information
+    assert sup._pick_devices(4) == [0, 1, 2, 3]
+
+
+def test_map_falls_back_to_a_loop_of_calls_on_cpu_backends():
+    remote = kt.fn(cases.summer, name="c-map").to(kt.Compute(cpus="1"))
+    try:
+        assert remote.map([]) == []
+        with pytest.raises(TypeError):
+            remote.map([(1, 2)])                           # one positional argument per item, like remote(x)
+    finally:
+        remote.teardown()
+    ident = kt.fn(cases.spmd_identity, name="c-map2").to(
+        kt.Compute(cpus="1", allowed_serialization=["json", "pickle"]).distribute("spmd", workers=1, num_proc=2))
+    try:
+        xs = [torch.arange(5.0) + i for i in range(3)]
+        out = ident.map(xs, serialization="pickle")
+        assert len(out) == 3 and all(len(o) == 2 and torch.equal(o[0], x) and torch.equal(o[1], x) for o, x in zip(out, xs))
+    finally:
+        ident.teardown()
+
+
+def test_broadcast_window_rendezvous_times_out_cleanly_without_a_putter(tmp_path, monkeypatch):
+    """The file rendezvous of a cross-process BroadcastWindow (no GPU needed up to the pull): a window that cannot
+    close raises on the participant and leaves no join file behind."""
+    from kubetorch_b200 import data_store
+
+    monkeypatch.setenv("KTB_STORE_DIR", str(tmp_path))
+    bw = kt.BroadcastWindow(world_size=3, timeout=0.2, group_id="cpu-bw")
+    with pytest.raises(kt.DataStoreError, match=r"timed out with 0 putter\(s\) and 1 getter\(s\)"):
+        data_store._join_shared("k", [("", torch.zeros(1))], bw, "get")
+    gdir = [p for p in tmp_path.iterdir() if p.name.startswith("bw_")]
+    assert gdir and not any(f.name.endswith(".join") for f in gdir[0].iterdir())
