@@ -187,6 +187,12 @@ def test_two_gpu_peer_path_matches_oracle():
         torch.cuda.synchronize(0)
         torch.cuda.synchronize(1)
         assert torch.equal(torch.cat(views).cpu(), single.cpu()), it
+    for engine in ("sm", "ce"):   # the scatter engines of the pushed form: capped scatter kernel / copy engines
+        mlp.SCATTER_ENGINE = engine
+        views = mlp.mlp_scatter_gather(obs, *w, devices=[0, 1], transfer="push")
+        torch.cuda.synchronize(0)
+        torch.cuda.synchronize(1)
+        assert torch.equal(torch.cat(views).cpu(), single.cpu()), engine
     g2 = torch.Generator().manual_seed(4)
     big = torch.randn(2 * 37888 + 2 * 1280, 256, generator=g2).bfloat16().cuda(0)   # several push chunks per rank, ragged tail
     ref_big = mlp.mlp_forward(big, *w)

@@ -388,3 +388,33 @@ def test_push_pipeline_emulated_on_one_gpu(K):
     sess.call(xi, yi, "scale", -3)
     torch.cuda.synchronize()
     assert torch.equal(yi.cpu(), xi.cpu() * -3)
+
+
+def test_numa_sharded_pinned_buffers_are_pinned_pooled_and_correct(K):
+    """kt.pinned_empty / ktb_host_alloc_sharded: page-locked (torch sees it as pinned), usable by the host pipeline,
+    returned to the pool when the last view dies and handed out again without a new allocation."""
+    import gc
+
+    import kubetorch_b200 as kt
+
+    n = (8 << 20) // 4 + 12345                       # > 4 MiB: the sharded allocator, ragged size
+    x = kt.pinned_empty((n,), torch.float32, gpus=1)
+    assert x.is_pinned() and not x.is_cuda and x.numel() == n
+    x.copy_(torch.arange(n, dtype=torch.float32))
+    y = K.map_host(x, "scale", 2.0, device=0)
+    assert torch.equal(y, x * 2)
+    ptr = x.data_ptr()
+    view = x[10:20]
+    del x
+    gc.collect()
+    assert view.data_ptr() == ptr + 40                # a living view keeps the block out of the pool
+    z = kt.pinned_empty((n,), torch.float32, gpus=1)
+    zptr = z.data_ptr()
+    assert zptr != ptr
+    del view, z
+    gc.collect()
+    again = kt.pinned_empty((n,), torch.float32, gpus=1)
+    assert again.data_ptr() in (ptr, zptr) and again.is_pinned()   # a pooled block is reused, nothing new is allocated
+    small = kt.pinned_empty((16,), torch.float32, gpus=1)          # small tensors come from torch's pinned allocator
+    assert small.is_pinned()
+    assert K.device_numa_node(0) >= -1
