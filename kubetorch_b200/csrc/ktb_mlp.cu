@@ -1448,7 +1448,9 @@ size_t ktb_mlp_stage_bytes(size_t M, int d_in) {
   return 2 * rows * (size_t)d_in * 2;
 }
 
-int g_mlp_stage_ce = 1;   // ktb_set_tuning(22, v): staged pulls by copy engine (1) or by a pull kernel (0)
+// ktb_set_tuning(22, v): staged pulls by a pull kernel (0, default) or by copy engine (1).  Measured at 8 GPUs
+// (profiles/r2j_c4_pull_ce_8gpu.log): copy-engine pulls 3.13 ms per call against 2.38 for the pull kernel
+int g_mlp_stage_ce = 0;
 
 static int mlp_run(int dev, const void* obs, size_t M, int d_in, int d_hidden, int d_out, const void* W1,
                    const void* W2, const void* W3, void* logits, void* scratch, void* stage, uintptr_t stream) {
