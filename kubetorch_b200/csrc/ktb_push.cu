@@ -136,8 +136,8 @@ __global__ void __launch_bounds__(kPushThreads)
   const uint32_t total_tiles = tiles_per_chunk * n_chunks;
   __shared__ bool flag;
   uint32_t have = 0;   // chunks [0, have) are known to have landed
-  // persistent grid, tiles in increasing order = chunk order; ONE system fence per CTA (before the ack ticket), not per
-  // tile: the fence waits for the acknowledgement of every peer store the CTA has in flight
+  // a slice of `slice` consecutive tiles per CTA (1 by default), tiles in increasing order = chunk order; one system
+  // fence per CTA before the ack ticket
   for (uint32_t base = blockIdx.x * slice; base < total_tiles; base += gridDim.x * slice)
   for (uint32_t tile = base; tile < min(total_tiles, base + slice); ++tile) {
     const uint32_t c = tile / tiles_per_chunk;
