@@ -38,6 +38,7 @@ std::atomic<int> g_mlp_cluster4_max[kMaxDevices];   // co-resident clusters of 4
 int g_mlp_fuse_head = 1;       // ktb_set_tuning key 18: 1 = layer 2 and the 64-wide head in one kernel (h2 stays on chip; default)
 int g_mlp_stages = 4;          // ktb_set_tuning key 17: TMA ring depth of the CTA-pair kernel (4 or 5)
 int g_mlp_cluster4 = 0;        // ktb_set_tuning key 15: 1 = cluster-of-4 multicast form of the CTA-pair kernel (opt-in)
+int g_mlp_l1_bres = 0;         // ktb_set_tuning key 24: 1 = B-resident layer-1 form of the CTA-pair kernel (K = 256)
 int g_mlp_2sm = 1;             // ktb_set_tuning key 11: 1 = CTA-pair (cta_group::2) kernel for the 256-wide layers (default)
 int g_mlp_tma_store = 1;       // ktb_set_tuning key 10: 1 = TMA-store epilogue for the 256-wide layers (default)
 int g_mlp_persistent = 1;      // ktb_set_tuning key 7: 1 = persistent double-buffered kernel, 0 = one tile per CTA
@@ -766,6 +767,186 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * EPI_GROUP
   }
 }
 
+// ---- layer-1 form of the CTA-pair kernel: K = 256 (4 k-blocks), B RESIDENT, A ring two tiles deep -------------------
+// With K = 256 a tile is four k-blocks and a 4-stage A+B ring is exactly one tile deep: stage s can be refilled for
+// tile t+1 only after MMA s of tile t has retired, so every tile exposes a TMA round trip (ncu r2e: 3.6 us per tile,
+// of which the MMAs are 1.1 us; DRAM 28 %, L2 34 %).  Here the pair walks tiles n-SLOWEST over a contiguous range, so
+// the 256-row slice of W1 it multiplies with stays in shared memory (64 KiB per CTA, reloaded only when the column
+// block changes, at most twice per launch) and the freed space makes the A ring AST x 16 KiB = 1.5 tiles deep (AST = 6)
+// beside the unchanged 64 KiB C staging tile.  MMA order inside a tile is the pair kernel's: results are bit-identical.
+template <int AST, bool RELU>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
+    gemm_bf16_tn_2sm_bres_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                 const __grid_constant__ CUtensorMap map_c, int tiles_m, int tiles_n) {
+  constexpr int BLOCK_N = 256;
+  constexpr int KB = 4;                                     // K = 256
+  constexpr int kABytes = kMlpBlockM * kMlpBlockK * 2;      // 16 KiB: this CTA's 128 rows of one A k-block
+  constexpr int kBBytes = 128 * kMlpBlockK * 2;             // 16 KiB: this CTA's half of one B k-block
+  constexpr int kCBytes = kMlpBlockM * BLOCK_N * 2;         // 64 KiB C tile of this CTA
+  constexpr int kBoxBytes = kMlpBlockM * 64 * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_ring = smem;
+  uint8_t* b_res = smem + AST * kABytes;
+  uint8_t* ctile = b_res + KB * kBBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ctile + kCBytes);   // [AST], used on the leader only
+  uint64_t* empty = full + AST;                                     // [AST], per CTA
+  uint64_t* tmem_full = empty + AST;                                // [2], per CTA
+  uint64_t* tmem_empty = tmem_full + 2;                             // [2], used on the leader only
+  uint64_t* b_full = tmem_empty + 2;                                // [1], used on the leader only
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(b_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  // contiguous range of the n-slowest tile enumeration t = n * tiles_m + m
+  const long long total = (long long)tiles_m * tiles_n;
+  const int t_begin = (int)(total * pair / num_pairs);
+  const int t_end = (int)(total * (pair + 1) / num_pairs);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+    prefetch_tensormap(&map_c);
+#pragma unroll
+    for (int s = 0; s < AST; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 8);
+    mbar_init(&tmem_empty[1], 8);
+    mbar_init(b_full, 1);
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 1) tmem_alloc_2sm(tmem_holder, 2 * BLOCK_N);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (lane == 0) {
+      int it = 0, cur_n = -1;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int n = t / tiles_m;
+        const int m0 = (t % tiles_m) * 256 + (int)rank * 128;
+        if (n != cur_n) {
+          // every MMA that reads the resident B has retired once the commit of the previous tile's last k-block arrived
+          if (it > 0) mbar_wait_bounded(&empty[(it - 1) % AST], ((it - 1) / AST) & 1);
+          if (leader) mbar_expect_tx(b_full, 2 * KB * kBBytes);
+          const uint32_t leader_b_full = smem_u32(b_full) & 0xFEFFFFFFu;
+          const int n0 = n * BLOCK_N + (int)rank * 128;
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) tma_load_2d_2sm(b_res + kb * kBBytes, &map_b, kb * kMlpBlockK, n0, leader_b_full);
+          cur_n = n;
+        }
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % AST;
+          mbar_wait_bounded(&empty[s], ((it / AST) & 1) ^ 1);
+          if (leader) mbar_expect_tx(&full[s], 2 * kABytes);
+          const uint32_t leader_full_tma = smem_u32(&full[s]) & 0xFEFFFFFFu;
+          tma_load_2d_2sm(a_ring + (size_t)s * kABytes, &map_a, kb * kMlpBlockK, m0, leader_full_tma);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N);
+      int it = 0, tt = 0, cur_n = -1, b_loads = 0;
+      for (int t = t_begin; t < t_end; ++t, ++tt) {
+        const int n = t / tiles_m;
+        const int as = tt & 1;
+        mbar_wait_bounded(&tmem_empty[as], ((tt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (n != cur_n) {
+          mbar_wait_bounded(b_full, b_loads & 1);
+          tc_fence_after();
+          ++b_loads;
+          cur_n = n;
+        }
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % AST;
+          mbar_wait_bounded(&full[s], (it / AST) & 1);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc_sw128(a_ring + (size_t)s * kABytes);
+          const uint64_t bdesc = make_smem_desc_sw128(b_res + kb * kBBytes);
+#pragma unroll
+          for (int k = 0; k < kMlpBlockK / kMlpUmmaK; ++k)
+            umma_f16_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          umma_commit_2sm(&empty[s]);          // A stage free in both CTAs
+        }
+        umma_commit_2sm(&tmem_full[as]);       // accumulator ready in both CTAs
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): own TMEM half → bf16 → swizzled shared C tile → TMA store (the pair kernel's) =====
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const bool issuer = (warp == 2 && lane == 0);
+    int tt = 0;
+    for (int t = t_begin; t < t_end; ++t, ++tt) {
+      const int as = tt & 1;
+      const int m0 = (t % tiles_m) * 256 + (int)rank * 128;
+      const int n0 = (t / tiles_m) * BLOCK_N;
+      mbar_wait_bounded(&tmem_full[as], (tt >> 1) & 1);
+      tc_fence_after();
+      if (issuer) bulk_wait_read<0>();
+      epi_barrier_n<128>();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c), acc);
+        uint8_t* box = ctile + (c >> 6) * kBoxBytes + row * 128;
+        const int chunk0 = (c & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float lo = __uint_as_float(acc[8 * q + 2 * j]);
+            float hi = __uint_as_float(acc[8 * q + 2 * j + 1]);
+            if (RELU) {
+              lo = fmaxf(lo, 0.f);
+              hi = fmaxf(hi, 0.f);
+            }
+            __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+            pk[j] = *reinterpret_cast<uint32_t*>(&v);
+          }
+          const int phys = (chunk0 + q) ^ (row & 7);
+          *reinterpret_cast<uint4*>(box + phys * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));   // leader's barrier
+      fence_proxy_async_smem();
+      epi_barrier_n<128>();
+      if (issuer) {
+#pragma unroll
+        for (int b = 0; b < BLOCK_N / 64; ++b) tma_store_2d(&map_c, ctile + b * kBoxBytes, n0 + 64 * b, m0);
+        bulk_commit();
+      }
+    }
+    if (issuer) bulk_wait_all<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 2 * BLOCK_N);
+  }
+}
+
 __device__ __forceinline__ void tma_load_2d_2sm_mc(void* smem_dst, const CUtensorMap* map, int c0, int c1,
                                                    uint32_t leader_bar_addr, uint16_t cta_mask) {
   // same CTA-relative destination offset and barrier offset in every CTA of cta_mask; with cta_group::2 and the peer bit
@@ -1327,6 +1508,19 @@ static int launch_gemm(int dev, const void* A, const void* B, void* C, size_t M,
     }
     const int tiles_m = (int)(M / 256), tiles_n = N / 256;
     const int grid = std::max(2, std::min(2 * tiles_m * tiles_n, sms & ~1));
+    if (K == 256 && g_mlp_l1_bres && g_mlp_epi_groups != 2) {
+      // layer 1 (K = 256): W1 slice resident, A ring 1.5 tiles deep (see gemm_bf16_tn_2sm_bres_kernel)
+      constexpr int AST = 6;
+      constexpr int smem_l1 = AST * 16384 + 4 * 16384 + kMlpBlockM * 256 * 2 + (2 * AST + 5) * 8 + 16 + 1024;
+      static_assert(smem_l1 <= 232448, "the B-resident layer-1 kernel must fit the opt-in shared memory limit");
+      auto kfn = gemm_bf16_tn_2sm_bres_kernel<AST, RELU>;
+      static std::atomic<unsigned> attr_done{0};
+      rc = ensure_smem_attr(kfn, smem_l1, attr_done, dev);
+      if (rc) return rc;
+      kfn<<<grid, 64 + 128, smem_l1, stream>>>(ma, mb2, mc, tiles_m, tiles_n);
+      KTB_CK(cudaGetLastError());
+      return KTB_OK;
+    }
     if (g_mlp_epi_groups == 2) {
       auto kfn = gemm_bf16_tn_2sm_kernel<ST, RELU, 2>;
       {
