@@ -97,6 +97,22 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// the same load WITHOUT the wait: the caller overlaps it with work on registers of an earlier load and issues
+// tmem_wait_ld() before touching r
+__device__ __forceinline__ void tmem_ld_32x32b_x32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major) | [32,46) SBO >> 4
 //   [46,48) version = 1 (sm_100) | [61,64) layout type = 2 (SWIZZLE_128B)
@@ -888,52 +904,72 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
       }
     }
   } else {
-    // ===== epilogue (both CTAs): own TMEM half → bf16 → swizzled shared C tile → TMA store (the pair kernel's) =====
+    // ===== epilogue (both CTAs): own TMEM half → bf16 → swizzled shared C tile → TMA store =====
+    // Two changes against the pair kernel's epilogue (same bytes, same rounding): (1) the tile leaves in two 128-column
+    // halves, each its own bulk group: the conversion of one half overlaps the TMA store of the other (before a half's
+    // boxes are rewritten only the store that read THEM, two groups back, has to be done: wait_group.read 1);
+    // (2) the TMEM loads are software-pipelined: the load of chunk j+1 is in flight while chunk j is converted.
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const bool issuer = (warp == 2 && lane == 0);
     int tt = 0;
+    auto convert = [&](const uint32_t (&acc)[32], int c) {
+      uint8_t* box = ctile + (c >> 6) * kBoxBytes + row * 128;
+      const int chunk0 = (c & 63) >> 3;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          float lo = __uint_as_float(acc[8 * q + 2 * jj]);
+          float hi = __uint_as_float(acc[8 * q + 2 * jj + 1]);
+          if (RELU) {
+            lo = fmaxf(lo, 0.f);
+            hi = fmaxf(hi, 0.f);
+          }
+          __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+          pk[jj] = *reinterpret_cast<uint32_t*>(&v);
+        }
+        const int phys = (chunk0 + q) ^ (row & 7);
+        *reinterpret_cast<uint4*>(box + phys * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    };
     for (int t = t_begin; t < t_end; ++t, ++tt) {
       const int as = tt & 1;
       const int m0 = (t % tiles_m) * 256 + (int)rank * 128;
       const int n0 = (t / tiles_m) * BLOCK_N;
       mbar_wait_bounded(&tmem_full[as], (tt >> 1) & 1);
       tc_fence_after();
-      if (issuer) bulk_wait_read<0>();
-      epi_barrier_n<128>();
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t acc[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c), acc);
-        uint8_t* box = ctile + (c >> 6) * kBoxBytes + row * 128;
-        const int chunk0 = (c & 63) >> 3;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t pk[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float lo = __uint_as_float(acc[8 * q + 2 * j]);
-            float hi = __uint_as_float(acc[8 * q + 2 * j + 1]);
-            if (RELU) {
-              lo = fmaxf(lo, 0.f);
-              hi = fmaxf(hi, 0.f);
-            }
-            __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-            pk[j] = *reinterpret_cast<uint32_t*>(&v);
-          }
-          const int phys = (chunk0 + q) ^ (row & 7);
-          *reinterpret_cast<uint4*>(box + phys * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      for (int h = 0; h < 2; ++h) {
+        uint32_t acc0[32], acc1[32];
+        tmem_ld_32x32b_x32_nowait(tbase + (uint32_t)(h * 128), acc0);      // in flight while the staging half drains
+        if (issuer) bulk_wait_read<1>();
+        epi_barrier_n<128>();
+        tmem_wait_ld();
+        tmem_ld_32x32b_x32_nowait(tbase + (uint32_t)(h * 128 + 32), acc1);
+        convert(acc0, h * 128);
+        tmem_wait_ld();
+        tmem_ld_32x32b_x32_nowait(tbase + (uint32_t)(h * 128 + 64), acc0);
+        convert(acc1, h * 128 + 32);
+        tmem_wait_ld();
+        tmem_ld_32x32b_x32_nowait(tbase + (uint32_t)(h * 128 + 96), acc1);
+        convert(acc0, h * 128 + 64);
+        tmem_wait_ld();
+        convert(acc1, h * 128 + 96);
+        if (h == 1) {                    // every TMEM read of this accumulator buffer is done
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));   // leader's barrier
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));   // leader's barrier
-      fence_proxy_async_smem();
-      epi_barrier_n<128>();
-      if (issuer) {
-#pragma unroll
-        for (int b = 0; b < BLOCK_N / 64; ++b) tma_store_2d(&map_c, ctile + b * kBoxBytes, n0 + 64 * b, m0);
-        bulk_commit();
+        fence_proxy_async_smem();
+        epi_barrier_n<128>();
+        if (issuer) {
+          tma_store_2d(&map_c, ctile + (2 * h) * kBoxBytes, n0 + 128 * h, m0);
+          tma_store_2d(&map_c, ctile + (2 * h + 1) * kBoxBytes, n0 + 128 * h + 64, m0);
+          bulk_commit();
+        }
       }
     }
     if (issuer) bulk_wait_all<0>();
