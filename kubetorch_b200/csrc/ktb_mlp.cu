@@ -38,7 +38,8 @@ std::atomic<int> g_mlp_cluster4_max[kMaxDevices];   // co-resident clusters of 4
 int g_mlp_fuse_head = 1;       // ktb_set_tuning key 18: 1 = layer 2 and the 64-wide head in one kernel (h2 stays on chip; default)
 int g_mlp_stages = 4;          // ktb_set_tuning key 17: TMA ring depth of the CTA-pair kernel (4 or 5)
 int g_mlp_cluster4 = 0;        // ktb_set_tuning key 15: 1 = cluster-of-4 multicast form of the CTA-pair kernel (opt-in)
-int g_mlp_l1_bres = 0;         // ktb_set_tuning key 24: 1 = B-resident layer-1 form of the CTA-pair kernel (K = 256)
+int g_mlp_l1_bres = 1;         // ktb_set_tuning key 24: 1 = layer-1 form of the CTA-pair kernel for K = 256 (default): W1 slice
+                               // resident, half-tile bulk groups + pipelined TMEM loads in the epilogue; bit-identical, +3 %
 int g_mlp_2sm = 1;             // ktb_set_tuning key 11: 1 = CTA-pair (cta_group::2) kernel for the 256-wide layers (default)
 int g_mlp_tma_store = 1;       // ktb_set_tuning key 10: 1 = TMA-store epilogue for the 256-wide layers (default)
 int g_mlp_persistent = 1;      // ktb_set_tuning key 7: 1 = persistent double-buffered kernel, 0 = one tile per CTA
