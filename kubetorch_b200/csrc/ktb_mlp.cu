@@ -791,10 +791,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * EPI_GROUP
 // the 256-row slice of W1 it multiplies with stays in shared memory (64 KiB per CTA, reloaded only when the column
 // block changes, at most twice per launch) and the freed space makes the A ring AST x 16 KiB = 1.5 tiles deep (AST = 6)
 // beside the unchanged 64 KiB C staging tile.  MMA order inside a tile is the pair kernel's: results are bit-identical.
-template <int AST, bool RELU>
+template <int AST, bool RELU, bool WARP_STORE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
     gemm_bf16_tn_2sm_bres_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                                 const __grid_constant__ CUtensorMap map_c, int tiles_m, int tiles_n) {
+                                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c32,
+                                 int tiles_m, int tiles_n) {
   constexpr int BLOCK_N = 256;
   constexpr int KB = 4;                                     // K = 256
   constexpr int kABytes = kMlpBlockM * kMlpBlockK * 2;      // 16 KiB: this CTA's 128 rows of one A k-block
@@ -828,6 +829,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
     prefetch_tensormap(&map_a);
     prefetch_tensormap(&map_b);
     prefetch_tensormap(&map_c);
+    prefetch_tensormap(&map_c32);
 #pragma unroll
     for (int s = 0; s < AST; ++s) {
       mbar_init(&full[s], 1);
@@ -946,8 +948,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
       for (int h = 0; h < 2; ++h) {
         uint32_t acc0[32], acc1[32];
         tmem_ld_32x32b_x32_nowait(tbase + (uint32_t)(h * 128), acc0);      // in flight while the staging half drains
-        if (issuer) bulk_wait_read<1>();
-        epi_barrier_n<128>();
+        if constexpr (WARP_STORE) {
+          // every epilogue warp owns its 32 rows end to end (own bulk groups, own TMA stores of 64 x 32 boxes): no
+          // CTA-wide barrier in the epilogue, a slow warp delays nobody
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+        } else {
+          if (issuer) bulk_wait_read<1>();
+          epi_barrier_n<128>();
+        }
         tmem_wait_ld();
         tmem_ld_32x32b_x32_nowait(tbase + (uint32_t)(h * 128 + 32), acc1);
         convert(acc0, h * 128);
@@ -965,15 +974,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
           if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));   // leader's barrier
         }
         fence_proxy_async_smem();
-        epi_barrier_n<128>();
-        if (issuer) {
-          tma_store_2d(&map_c, ctile + (2 * h) * kBoxBytes, n0 + 128 * h, m0);
-          tma_store_2d(&map_c, ctile + (2 * h + 1) * kBoxBytes, n0 + 128 * h + 64, m0);
-          bulk_commit();
+        if constexpr (WARP_STORE) {
+          __syncwarp();
+          if (lane == 0) {
+            const int r0 = quarter * 32;          // this warp's rows inside the CTA's 128
+            tma_store_2d(&map_c32, ctile + (2 * h) * kBoxBytes + r0 * 128, n0 + 128 * h, m0 + r0);
+            tma_store_2d(&map_c32, ctile + (2 * h + 1) * kBoxBytes + r0 * 128, n0 + 128 * h + 64, m0 + r0);
+            bulk_commit();
+          }
+        } else {
+          epi_barrier_n<128>();
+          if (issuer) {
+            tma_store_2d(&map_c, ctile + (2 * h) * kBoxBytes, n0 + 128 * h, m0);
+            tma_store_2d(&map_c, ctile + (2 * h + 1) * kBoxBytes, n0 + 128 * h + 64, m0);
+            bulk_commit();
+          }
         }
       }
     }
-    if (issuer) bulk_wait_all<0>();
+    if (WARP_STORE ? (lane == 0) : issuer) bulk_wait_all<0>();
   }
 
   tc_fence_before();
@@ -1550,11 +1569,22 @@ static int launch_gemm(int dev, const void* A, const void* B, void* C, size_t M,
       constexpr int AST = 6;
       constexpr int smem_l1 = AST * 16384 + 4 * 16384 + kMlpBlockM * 256 * 2 + (2 * AST + 5) * 8 + 16 + 1024;
       static_assert(smem_l1 <= 232448, "the B-resident layer-1 kernel must fit the opt-in shared memory limit");
-      auto kfn = gemm_bf16_tn_2sm_bres_kernel<AST, RELU>;
-      static std::atomic<unsigned> attr_done{0};
-      rc = ensure_smem_attr(kfn, smem_l1, attr_done, dev);
+      CUtensorMap mc32;
+      rc = make_map(&mc32, C, M, (uint64_t)N, 32);      // per-warp stores: 64 columns x 32 rows
       if (rc) return rc;
-      kfn<<<grid, 64 + 128, smem_l1, stream>>>(ma, mb2, mc, tiles_m, tiles_n);
+      if (g_mlp_l1_bres == 2) {
+        auto kfn = gemm_bf16_tn_2sm_bres_kernel<AST, RELU, true>;
+        static std::atomic<unsigned> attr_done{0};
+        rc = ensure_smem_attr(kfn, smem_l1, attr_done, dev);
+        if (rc) return rc;
+        kfn<<<grid, 64 + 128, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n);
+      } else {
+        auto kfn = gemm_bf16_tn_2sm_bres_kernel<AST, RELU, false>;
+        static std::atomic<unsigned> attr_done{0};
+        rc = ensure_smem_attr(kfn, smem_l1, attr_done, dev);
+        if (rc) return rc;
+        kfn<<<grid, 64 + 128, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n);
+      }
       KTB_CK(cudaGetLastError());
       return KTB_OK;
     }
