@@ -384,7 +384,7 @@ int ktb_set_tuning(int key, int value) {
     case 14: g_red_fold = value ? 1 : 0; return KTB_OK;
     case 18: g_mlp_fuse_head = value ? 1 : 0; return KTB_OK;
     case 20: g_host_zero_copy = value ? 1 : 0; return KTB_OK;
-    case 24: g_mlp_l1_bres = (value >= 0 && value <= 2) ? value : 1; return KTB_OK;   // 2 = per-warp stores
+    case 24: g_mlp_l1_bres = (value >= 0 && value <= 3) ? value : 2; return KTB_OK;   // 2 = per-warp stores, 3 = + 8 epilogue warps
     case 23: g_push_slice = value > 0 ? value : 1; return KTB_OK;
     case 22: g_mlp_stage_ce = value ? 1 : 0; return KTB_OK;
     case 21: g_push_scatter_ctas_per_sm = value > 0 ? value : 0; return KTB_OK;

@@ -38,7 +38,7 @@ std::atomic<int> g_mlp_cluster4_max[kMaxDevices];   // co-resident clusters of 4
 int g_mlp_fuse_head = 1;       // ktb_set_tuning key 18: 1 = layer 2 and the 64-wide head in one kernel (h2 stays on chip; default)
 int g_mlp_stages = 4;          // ktb_set_tuning key 17: TMA ring depth of the CTA-pair kernel (4 or 5)
 int g_mlp_cluster4 = 0;        // ktb_set_tuning key 15: 1 = cluster-of-4 multicast form of the CTA-pair kernel (opt-in)
-int g_mlp_l1_bres = 1;         // ktb_set_tuning key 24: 1 = layer-1 form of the CTA-pair kernel for K = 256 (default): W1 slice
+int g_mlp_l1_bres = 2;         // ktb_set_tuning key 24: 1 = layer-1 form of the CTA-pair kernel for K = 256 (default): W1 slice
                                // resident, half-tile bulk groups + pipelined TMEM loads in the epilogue; bit-identical, +3 %
 int g_mlp_2sm = 1;             // ktb_set_tuning key 11: 1 = CTA-pair (cta_group::2) kernel for the 256-wide layers (default)
 int g_mlp_tma_store = 1;       // ktb_set_tuning key 10: 1 = TMA-store epilogue for the 256-wide layers (default)
@@ -791,8 +791,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * EPI_GROUP
 // the 256-row slice of W1 it multiplies with stays in shared memory (64 KiB per CTA, reloaded only when the column
 // block changes, at most twice per launch) and the freed space makes the A ring AST x 16 KiB = 1.5 tiles deep (AST = 6)
 // beside the unchanged 64 KiB C staging tile.  MMA order inside a tile is the pair kernel's: results are bit-identical.
-template <int AST, bool RELU, bool WARP_STORE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
+template <int AST, bool RELU, bool WARP_STORE, int EPI_WARPS = 4>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS, 1)
     gemm_bf16_tn_2sm_bres_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                  const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c32,
                                  int tiles_m, int tiles_n) {
@@ -837,8 +837,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
     }
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], 8);
-    mbar_init(&tmem_empty[1], 8);
+    mbar_init(&tmem_empty[0], 2 * EPI_WARPS);     // one arrival per epilogue warp of both CTAs
+    mbar_init(&tmem_empty[1], 2 * EPI_WARPS);
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
@@ -944,14 +944,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
       mbar_wait_bounded(&tmem_full[as], (tt >> 1) & 1);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N);
+      // EPI_WARPS == 8: warps 2-5 own the first 128 columns, warps 6-9 the second (a warp reaches the TMEM lanes of
+      // quarter warp % 4 only, so warps w and w + 4 share a quarter); each warp does ONE half per tile
+      const int h_begin = (EPI_WARPS == 8) ? ((warp - 2) >> 2) : 0;
+      const int h_end = (EPI_WARPS == 8) ? h_begin + 1 : 2;
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
+      for (int h = h_begin; h < h_end; ++h) {
         uint32_t acc0[32], acc1[32];
         tmem_ld_32x32b_x32_nowait(tbase + (uint32_t)(h * 128), acc0);      // in flight while the staging half drains
         if constexpr (WARP_STORE) {
           // every epilogue warp owns its 32 rows end to end (own bulk groups, own TMA stores of 64 x 32 boxes): no
           // CTA-wide barrier in the epilogue, a slow warp delays nobody
-          if (lane == 0) bulk_wait_read<1>();
+          if (lane == 0) {
+            if constexpr (EPI_WARPS == 8) bulk_wait_read<0>(); else bulk_wait_read<1>();
+          }
           __syncwarp();
         } else {
           if (issuer) bulk_wait_read<1>();
@@ -968,7 +974,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
         convert(acc0, h * 128 + 64);
         tmem_wait_ld();
         convert(acc1, h * 128 + 96);
-        if (h == 1) {                    // every TMEM read of this accumulator buffer is done
+        if (h == h_end - 1) {            // every TMEM read of this warp from this accumulator buffer is done
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));   // leader's barrier
@@ -1572,7 +1578,13 @@ static int launch_gemm(int dev, const void* A, const void* B, void* C, size_t M,
       CUtensorMap mc32;
       rc = make_map(&mc32, C, M, (uint64_t)N, 32);      // per-warp stores: 64 columns x 32 rows
       if (rc) return rc;
-      if (g_mlp_l1_bres == 2) {
+      if (g_mlp_l1_bres == 3) {
+        auto kfn = gemm_bf16_tn_2sm_bres_kernel<AST, RELU, true, 8>;
+        static std::atomic<unsigned> attr_done{0};
+        rc = ensure_smem_attr(kfn, smem_l1, attr_done, dev);
+        if (rc) return rc;
+        kfn<<<grid, 64 + 256, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n);
+      } else if (g_mlp_l1_bres == 2) {
         auto kfn = gemm_bf16_tn_2sm_bres_kernel<AST, RELU, true>;
         static std::atomic<unsigned> attr_done{0};
         rc = ensure_smem_attr(kfn, smem_l1, attr_done, dev);

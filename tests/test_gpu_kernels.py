@@ -342,7 +342,10 @@ def test_mlp_tcgen05_matches_recorded_reference_and_fp32(K, golden):
         K.set_tuning(9, 1)
         K.set_tuning(24, 0)  # layer 1 through the generic pair kernel instead of its K = 256 form: same bits
         assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got2)
-        K.set_tuning(24, 1)
+        for v in (1, 3):     # layer-1 kernel with CTA-wide stores / with eight epilogue warps: same bits
+            K.set_tuning(24, v)
+            assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got2)
+        K.set_tuning(24, 2)
         K.set_tuning(17, 5)  # five-stage TMA ring: same bits
         assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got2)
         K.set_tuning(17, 4)
@@ -356,12 +359,12 @@ def test_mlp_tcgen05_matches_recorded_reference_and_fp32(K, golden):
         K.set_tuning(7, 0)  # one-tile-per-CTA kernel: same bits
         assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got2)
     finally:  # back to the shipped defaults for whatever runs next in this process
-        for key, val in ((7, 1), (8, 75776), (9, 1), (10, 1), (11, 1), (15, 0), (17, 4), (18, 1), (24, 1)):
+        for key, val in ((7, 1), (8, 75776), (9, 1), (10, 1), (11, 1), (15, 0), (17, 4), (18, 1), (24, 2)):
             K.set_tuning(key, val)
     # the fused kernel with several chunks and with the staged pull: same bits as the one-chunk fused call
     K.set_tuning(24, 0)   # the fused default with layer 1 on the generic pair kernel: same bits as the shipped default
     assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got_fused)
-    K.set_tuning(24, 1)
+    K.set_tuning(24, 2)
     K.set_tuning(8, 4096)
     try:
         assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got_fused)
