@@ -38,6 +38,9 @@ std::atomic<int> g_mlp_cluster4_max[kMaxDevices];   // co-resident clusters of 4
 int g_mlp_fuse_head = 1;       // ktb_set_tuning key 18: 1 = layer 2 and the 64-wide head in one kernel (h2 stays on chip; default)
 int g_mlp_stages = 4;          // ktb_set_tuning key 17: TMA ring depth of the CTA-pair kernel (4 or 5)
 int g_mlp_cluster4 = 0;        // ktb_set_tuning key 15: 1 = cluster-of-4 multicast form of the CTA-pair kernel (opt-in)
+int g_mlp_arrive_mode = 1;     // ktb_set_tuning key 25: semantics of the epilogue's remote mbarrier arrives (see mbar_arrive_remote):
+                               // 0 = release.cluster everywhere, 1 = CTA-scope release for the TMEM hand-backs (default: +6 %,
+                               // profiles/r2n_probe_arrive.log), 2 = also for c_ready; bit 2 = pipelined TMEM loads in the fused epilogue
 int g_mlp_l1_bres = 2;         // ktb_set_tuning key 24: 1 = layer-1 form of the CTA-pair kernel for K = 256 (default): W1 slice
                                // resident, half-tile bulk groups + pipelined TMEM loads in the epilogue; bit-identical, +3 %
 int g_mlp_2sm = 1;             // ktb_set_tuning key 11: 1 = CTA-pair (cta_group::2) kernel for the 256-wide layers (default)
@@ -570,6 +573,19 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t ran
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Remote arrive whose only job is to hand a TMEM buffer back (ordering comes from tcgen05.fence::before_thread_sync):
+// `.release.cluster` makes ptxas emit MEMBAR.ALL.GPU + ERRBAR in front of the arrive — the issuing lane then waits for
+// every global write it has in flight, TMA stores included — while the default semantics (release at CTA scope) cost a
+// MEMBAR.ALL.CTA.  mode 0 keeps the cluster-scope release (ktb_set_tuning key 25).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr, int cta_sem) {
+  if (cta_sem)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  else
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr),
                "r"(bytes)
@@ -795,7 +811,7 @@ template <int AST, bool RELU, bool WARP_STORE, int EPI_WARPS = 4>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS, 1)
     gemm_bf16_tn_2sm_bres_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                  const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c32,
-                                 int tiles_m, int tiles_n) {
+                                 int tiles_m, int tiles_n, int arrive_mode) {
   constexpr int BLOCK_N = 256;
   constexpr int KB = 4;                                     // K = 256
   constexpr int kABytes = kMlpBlockM * kMlpBlockK * 2;      // 16 KiB: this CTA's 128 rows of one A k-block
@@ -915,9 +931,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const bool issuer = (warp == 2 && lane == 0);
+    const uint32_t ctile_s = smem_u32(ctile);
     int tt = 0;
     auto convert = [&](const uint32_t (&acc)[32], int c) {
-      uint8_t* box = ctile + (c >> 6) * kBoxBytes + row * 128;
+      const uint32_t box = ctile_s + (uint32_t)((c >> 6) * kBoxBytes + row * 128);
       const int chunk0 = (c & 63) >> 3;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -934,7 +951,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
           pk[jj] = *reinterpret_cast<uint32_t*>(&v);
         }
         const int phys = (chunk0 + q) ^ (row & 7);
-        *reinterpret_cast<uint4*>(box + phys * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        st_shared_v4(box + (uint32_t)(phys * 16), pk[0], pk[1], pk[2], pk[3]);     // STS.128, not a generic store
       }
     };
     for (int t = t_begin; t < t_end; ++t, ++tt) {
@@ -977,7 +994,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
         if (h == h_end - 1) {            // every TMEM read of this warp from this accumulator buffer is done
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));   // leader's barrier
+          if (lane == 0) mbar_arrive_remote(map_to_cta(smem_u32(&tmem_empty[as]), 0), arrive_mode & 3);   // leader's barrier
         }
         fence_proxy_async_smem();
         if constexpr (WARP_STORE) {
@@ -1223,7 +1240,7 @@ template <int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
     mlp_l2_head_fused_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                              const __grid_constant__ CUtensorMap map_w3, __nv_bfloat16* __restrict__ out, int ldo,
-                             int K, int tiles_m, int tiles_n) {
+                             int K, int tiles_m, int tiles_n, int arrive_mode) {
   constexpr int BLOCK_N = 256;
   constexpr int kABytes = kMlpBlockM * kMlpBlockK * 2;      // 16 KiB: this CTA's 128 rows of A
   constexpr int kBBytes = 128 * kMlpBlockK * 2;             // 16 KiB: this CTA's half of the W2 tile
@@ -1363,17 +1380,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
 #pragma unroll
     for (int i = 0; i < 64; ++i) acc3[i] = 0.f;
     const uint32_t leader_c_ready = map_to_cta(smem_u32(c_ready), 0);
+    const uint32_t ctile_s = smem_u32(ctile);
     for (int t = 0; t < T; ++t) {
       const int as = t & 1;
       const int tn = t % tiles_n;
       // ---- part 1: relu(accumulator) -> bf16 -> swizzled C tile (the head's A operand) ----
       mbar_wait_bounded(&tmem_full[as], (t >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t acc[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c), acc);
-        uint8_t* box = ctile + (c >> 6) * kBoxBytes + row * 128;
+      const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N);
+      auto convert = [&](const uint32_t (&acc)[32], int c) {
+        const uint32_t box = ctile_s + (uint32_t)((c >> 6) * kBoxBytes + row * 128);
         const int chunk0 = (c & 63) >> 3;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -1386,13 +1402,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
             pk[j] = *reinterpret_cast<uint32_t*>(&v);
           }
           const int phys = (chunk0 + q) ^ (row & 7);
-          *reinterpret_cast<uint4*>(box + phys * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          st_shared_v4(box + (uint32_t)(phys * 16), pk[0], pk[1], pk[2], pk[3]);
+        }
+      };
+      if (arrive_mode & 4) {
+        // software-pipelined TMEM loads: chunk j+1 is in flight while chunk j is converted (same bytes, same rounding)
+        uint32_t acc0[32], acc1[32];
+        tmem_ld_32x32b_x32_nowait(tacc, acc0);
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 64) {
+          tmem_wait_ld();
+          tmem_ld_32x32b_x32_nowait(tacc + (uint32_t)(c + 32), acc1);
+          convert(acc0, c);
+          tmem_wait_ld();
+          if (c + 64 < BLOCK_N) tmem_ld_32x32b_x32_nowait(tacc + (uint32_t)(c + 64), acc0);
+          convert(acc1, c + 32);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(tacc + (uint32_t)c, acc);
+          convert(acc, c);
         }
       }
       tc_fence_before();
       fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(leader_c_ready);
+      // mode 2 also drops the cluster-scope release here: the C tile is read by THIS CTA's tensor core (async proxy,
+      // ordered by the proxy fence above), the leader only needs to learn that it may issue
+      if (lane == 0) mbar_arrive_remote(leader_c_ready, (arrive_mode & 3) >= 2);
       // ---- part 2: head partial (64 columns) -> fp32 registers; the accumulator buffer is free afterwards ----
       mbar_wait_bounded(l3_full, (uint32_t)(t & 1));
       tc_fence_after();
@@ -1405,7 +1444,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));
+      if (lane == 0) mbar_arrive_remote(map_to_cta(smem_u32(&tmem_empty[as]), 0), (arrive_mode & 3) >= 1);
       if (tn == tiles_n - 1) {
         const int unit = pair + (t / tiles_n) * num_pairs;
         const size_t grow = (size_t)unit * 256 + (size_t)rank * 128 + (size_t)row;
@@ -1583,19 +1622,19 @@ static int launch_gemm(int dev, const void* A, const void* B, void* C, size_t M,
         static std::atomic<unsigned> attr_done{0};
         rc = ensure_smem_attr(kfn, smem_l1, attr_done, dev);
         if (rc) return rc;
-        kfn<<<grid, 64 + 256, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n);
+        kfn<<<grid, 64 + 256, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n, g_mlp_arrive_mode);
       } else if (g_mlp_l1_bres == 2) {
         auto kfn = gemm_bf16_tn_2sm_bres_kernel<AST, RELU, true>;
         static std::atomic<unsigned> attr_done{0};
         rc = ensure_smem_attr(kfn, smem_l1, attr_done, dev);
         if (rc) return rc;
-        kfn<<<grid, 64 + 128, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n);
+        kfn<<<grid, 64 + 128, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n, g_mlp_arrive_mode);
       } else {
         auto kfn = gemm_bf16_tn_2sm_bres_kernel<AST, RELU, false>;
         static std::atomic<unsigned> attr_done{0};
         rc = ensure_smem_attr(kfn, smem_l1, attr_done, dev);
         if (rc) return rc;
-        kfn<<<grid, 64 + 128, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n);
+        kfn<<<grid, 64 + 128, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n, g_mlp_arrive_mode);
       }
       KTB_CK(cudaGetLastError());
       return KTB_OK;
@@ -1701,7 +1740,7 @@ static int launch_l2_head_fused(int dev, const void* h1, const void* W2, const v
   const int sms = device_info(dev) ? device_info(dev)->sm_count : 148;
   const int grid = 2 * std::max(1, std::min(tiles_m, sms / 2));
   kfn<<<grid, 64 + 128, smem_bytes, stream>>>(ma, mb, mw3, static_cast<__nv_bfloat16*>(logits), d_out, d_hidden, tiles_m,
-                                              tiles_n);
+                                              tiles_n, g_mlp_arrive_mode);
   KTB_CK(cudaGetLastError());
   return KTB_OK;
 }
