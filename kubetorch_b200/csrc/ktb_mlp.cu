@@ -38,6 +38,10 @@ std::atomic<int> g_mlp_cluster4_max[kMaxDevices];   // co-resident clusters of 4
 int g_mlp_fuse_head = 1;       // ktb_set_tuning key 18: 1 = layer 2 and the 64-wide head in one kernel (h2 stays on chip; default)
 int g_mlp_stages = 4;          // ktb_set_tuning key 17: TMA ring depth of the CTA-pair kernel (4 or 5)
 int g_mlp_cluster4 = 0;        // ktb_set_tuning key 15: 1 = cluster-of-4 multicast form of the CTA-pair kernel (opt-in)
+unsigned long long* g_mlp_trace = nullptr;   // ktb_debug_set_ptr(0, p): device buffer of 16 x 64 clock64() stamps (layer-1 kernel)
+int g_mlp_debug_flags = 0;     // ktb_debug_set_ptr(1, flags): bit 3 = layer-1 kernel issues no TMA stores (timing diagnostic, wrong results)
+int g_mlp_pf = 0;              // ktb_set_tuning key 26: low 4 bits = L2 prefetch distance (tiles) of the layer-1 kernel's A operand,
+                               // bit 4 = prefetch the next row block's h1 in the fused kernel
 int g_mlp_arrive_mode = 1;     // ktb_set_tuning key 25: semantics of the epilogue's remote mbarrier arrives (see mbar_arrive_remote):
                                // 0 = release.cluster everywhere, 1 = CTA-scope release for the TMEM hand-backs (default: +6 %,
                                // profiles/r2n_probe_arrive.log), 2 = also for c_ready; bit 2 = pipelined TMEM loads in the fused epilogue
@@ -565,6 +569,13 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Execution-only cluster barrier (no release/acquire: ptxas emits no MEMBAR.ALL.GPU): enough for "nobody exits while
+// the peer may still touch my shared memory / barriers".
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  __syncwarp();
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
@@ -614,6 +625,10 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       "l"(map), "r"(leader_bar_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 prefetch of one TMA box (no shared memory, no barrier): the later cp.async.bulk.tensor of the same box hits L2
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
@@ -624,6 +639,19 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, ui
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// one lane of a CONVERGED warp (elect.sync).  The MMA issuer runs its loops with the whole warp so that the operands of
+// tcgen05.mma stay warp-uniform for the compiler: issued from an `if (lane == 0)` region, every UTCHMMA / UTCBAR is
+// wrapped in an ELECT + 5 x R2UR.BROADCAST + BRA.U.ANY waterfall loop and the single thread issues one MMA per ~177
+// cycles against the 128 the tensor pipe needs for a 256x256x16 step (tools/probe_trace.py).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n.reg .b32 rx;\n.reg .pred px;\n"
+      "elect.sync rx|px, 0xFFFFFFFF;\n"
+      "selp.b32 %0, 1, 0, px;\n}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrives on `bar` in BOTH CTAs of the pair
   asm volatile(
@@ -807,16 +835,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * EPI_GROUP
 // the 256-row slice of W1 it multiplies with stays in shared memory (64 KiB per CTA, reloaded only when the column
 // block changes, at most twice per launch) and the freed space makes the A ring AST x 16 KiB = 1.5 tiles deep (AST = 6)
 // beside the unchanged 64 KiB C staging tile.  MMA order inside a tile is the pair kernel's: results are bit-identical.
-template <int AST, bool RELU, bool WARP_STORE, int EPI_WARPS = 4>
+template <int AST, bool RELU, int STORE, int EPI_WARPS = 4>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS, 1)
     gemm_bf16_tn_2sm_bres_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                  const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c32,
-                                 int tiles_m, int tiles_n, int arrive_mode) {
+                                 int tiles_m, int tiles_n, int arrive_mode, int pf_tiles,
+                                 unsigned long long* trace) {
+  // trace (developer tool, tools/probe_trace.py; nullptr in every product call): the leader CTA of pair 0 records
+  // clock64() at the hand-offs of its first 64 tiles, trace[event * 64 + tile]
+#define KTB_TR(ev, tile) \
+  do { if (trace != nullptr && blockIdx.x == 0) trace[(ev) * 64 + ((tile) & 63)] = (unsigned long long)clock64(); } while (0)
+#define KTB_TG(k) \
+  do { if (trace != nullptr && threadIdx.x == 0) trace[1024 + blockIdx.x * 4 + (k)] = globaltimer_ns(); } while (0)
+  KTB_TG(0);
   constexpr int BLOCK_N = 256;
   constexpr int KB = 4;                                     // K = 256
   constexpr int kABytes = kMlpBlockM * kMlpBlockK * 2;      // 16 KiB: this CTA's 128 rows of one A k-block
   constexpr int kBBytes = 128 * kMlpBlockK * 2;             // 16 KiB: this CTA's half of one B k-block
-  constexpr int kCBytes = kMlpBlockM * BLOCK_N * 2;         // 64 KiB C tile of this CTA
+  // STORE: 0 = one thread stores 128 x 64 boxes, 1 = every epilogue warp stores its own 32 rows in two 128-column
+  // halves (64 KiB staging), 2 = in four 64-column boxes rotating through 8 KiB per warp (32 KiB staging: the other
+  // 32 KiB go to the A ring, which the measured 1.9 us TMA latency under this kernel's own write stream needs)
+  constexpr bool WARP_STORE = STORE >= 1;
+  constexpr int kCBytes = (STORE == 2) ? kMlpBlockM * BLOCK_N : kMlpBlockM * BLOCK_N * 2;   // 32 / 64 KiB C staging
   constexpr int kBoxBytes = kMlpBlockM * 64 * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -864,6 +904,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  KTB_TG(1);
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs) =====
@@ -872,6 +913,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
       for (int t = t_begin; t < t_end; ++t) {
         const int n = t / tiles_m;
         const int m0 = (t % tiles_m) * 256 + (int)rank * 128;
+        KTB_TR(8, t - t_begin);
+        if (pf_tiles > 0) {
+          // the A tiles stream from HBM once, under 3.5 TB/s of h1 writes: a TMA load takes ~1.9 us from issue to
+          // barrier (tools/probe_trace.py), longer than the 1.5-tile ring covers; an L2 prefetch pf_tiles ahead hides it
+          const int first = (t == t_begin) ? t + 1 : t + pf_tiles;
+          for (int u = first; u <= t + pf_tiles && u < t_end; ++u) {
+            const int um0 = (u % tiles_m) * 256 + (int)rank * 128;
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) tma_prefetch_2d(&map_a, kb * kMlpBlockK, um0);
+          }
+        }
         if (n != cur_n) {
           // every MMA that reads the resident B has retired once the commit of the previous tile's last k-block arrived
           if (it > 0) mbar_wait_bounded(&empty[(it - 1) % AST], ((it - 1) / AST) & 1);
@@ -889,11 +941,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
           const uint32_t leader_full_tma = smem_u32(&full[s]) & 0xFEFFFFFFu;
           tma_load_2d_2sm(a_ring + (size_t)s * kABytes, &map_a, kb * kMlpBlockK, m0, leader_full_tma);
         }
+        KTB_TR(9, t - t_begin);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only) =====
-    if (leader && lane == 0) {
+    if (leader) {                     // the WHOLE warp walks the loops (uniform operands), one elected lane issues
       constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N);
       int it = 0, tt = 0, cur_n = -1, b_loads = 0;
       for (int t = t_begin; t < t_end; ++t, ++tt) {
@@ -901,6 +954,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
         const int as = tt & 1;
         mbar_wait_bounded(&tmem_empty[as], ((tt >> 1) & 1) ^ 1);
         tc_fence_after();
+        if (lane == 0) KTB_TR(0, tt);
         if (n != cur_n) {
           mbar_wait_bounded(b_full, b_loads & 1);
           tc_fence_after();
@@ -912,14 +966,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
           const int s = it % AST;
           mbar_wait_bounded(&full[s], (it / AST) & 1);
           tc_fence_after();
+          if (trace != nullptr && lane == 0) {
+            if (kb == 0) KTB_TR(1, tt);
+            if (kb == 1) KTB_TR(12, tt);
+            if (kb == 2) KTB_TR(13, tt);
+            if (kb == KB - 1) KTB_TR(2, tt);
+          }
           const uint64_t adesc = make_smem_desc_sw128(a_ring + (size_t)s * kABytes);
           const uint64_t bdesc = make_smem_desc_sw128(b_res + kb * kBBytes);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < kMlpBlockK / kMlpUmmaK; ++k)
-            umma_f16_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-          umma_commit_2sm(&empty[s]);          // A stage free in both CTAs
+            for (int k = 0; k < kMlpBlockK / kMlpUmmaK; ++k)
+              umma_f16_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            umma_commit_2sm(&empty[s]);          // A stage free in both CTAs
+            if (kb == KB - 1) umma_commit_2sm(&tmem_full[as]);       // accumulator ready in both CTAs
+          }
+          __syncwarp();
         }
-        umma_commit_2sm(&tmem_full[as]);       // accumulator ready in both CTAs
+        if (lane == 0) KTB_TR(3, tt);
       }
     }
   } else {
@@ -954,12 +1018,74 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
         st_shared_v4(box + (uint32_t)(phys * 16), pk[0], pk[1], pk[2], pk[3]);     // STS.128, not a generic store
       }
     };
+    if constexpr (STORE == 2) {
+      // four bulk groups per tile and warp: group g = columns [64g, 64g + 64) -> box g & 1 of this warp's 8 KiB
+      // (32 rows x 128 B, SWIZZLE_128B) -> one TMA store; a box is rewritten once the group two back has been read
+      const uint32_t cwarp = ctile_s + (uint32_t)(quarter * 8192 + lane * 128);
+      auto convert_q = [&](const uint32_t (&acc)[32], uint32_t boxrow, int chunk0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            float lo = __uint_as_float(acc[8 * q + 2 * jj]);
+            float hi = __uint_as_float(acc[8 * q + 2 * jj + 1]);
+            if (RELU) {
+              lo = fmaxf(lo, 0.f);
+              hi = fmaxf(hi, 0.f);
+            }
+            __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+            pk[jj] = *reinterpret_cast<uint32_t*>(&v);
+          }
+          const int phys = (chunk0 + q) ^ (lane & 7);
+          st_shared_v4(boxrow + (uint32_t)(phys * 16), pk[0], pk[1], pk[2], pk[3]);
+        }
+      };
+      for (int t = t_begin; t < t_end; ++t, ++tt) {
+        const int as = tt & 1;
+        const int m0 = (t % tiles_m) * 256 + (int)rank * 128 + quarter * 32;
+        const int n0 = (t / tiles_m) * BLOCK_N;
+        mbar_wait_bounded(&tmem_full[as], (tt >> 1) & 1);
+        tc_fence_after();
+        if (warp == 2 && lane == 0) KTB_TR(4, tt);
+        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N);
+        uint32_t acc0[32], acc1[32];
+        tmem_ld_32x32b_x32_nowait(tbase, acc0);
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          const uint32_t boxrow = cwarp + (uint32_t)((g & 1) * 4096);
+          tmem_wait_ld();
+          tmem_ld_32x32b_x32_nowait(tbase + (uint32_t)(64 * g + 32), acc1);
+          convert_q(acc0, boxrow, 0);
+          tmem_wait_ld();
+          if (g < 3) tmem_ld_32x32b_x32_nowait(tbase + (uint32_t)(64 * g + 64), acc0);
+          convert_q(acc1, boxrow, 4);
+          if (g == 3) {                  // every TMEM read of this warp from this accumulator buffer is done
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(map_to_cta(smem_u32(&tmem_empty[as]), 0), arrive_mode & 3);
+            if (warp == 2 && lane == 0) KTB_TR(6, tt);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && !(arrive_mode & 8)) {
+            tma_store_2d(&map_c32, ctile + quarter * 8192 + (g & 1) * 4096, n0 + 64 * g, m0);
+            bulk_commit();
+            if (warp == 2 && g == 3) KTB_TR(7, tt);
+          }
+        }
+      }
+      if (lane == 0) { if (arrive_mode & 16) bulk_wait_all<0>(); else bulk_wait_read<0>(); }
+    } else {
     for (int t = t_begin; t < t_end; ++t, ++tt) {
       const int as = tt & 1;
       const int m0 = (t % tiles_m) * 256 + (int)rank * 128;
       const int n0 = (t / tiles_m) * BLOCK_N;
       mbar_wait_bounded(&tmem_full[as], (tt >> 1) & 1);
       tc_fence_after();
+      if (warp == 2 && lane == 0) KTB_TR(4, tt);
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N);
       // EPI_WARPS == 8: warps 2-5 own the first 128 columns, warps 6-9 the second (a warp reaches the TMEM lanes of
       // quarter warp % 4 only, so warps w and w + 4 share a quarter); each warp does ONE half per tile
@@ -976,6 +1102,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
             if constexpr (EPI_WARPS == 8) bulk_wait_read<0>(); else bulk_wait_read<1>();
           }
           __syncwarp();
+          if (warp == 2 && lane == 0) KTB_TR(10 + h, tt);
         } else {
           if (issuer) bulk_wait_read<1>();
           epi_barrier_n<128>();
@@ -991,19 +1118,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
         convert(acc0, h * 128 + 64);
         tmem_wait_ld();
         convert(acc1, h * 128 + 96);
+        if (warp == 2 && lane == 0 && h == 0) KTB_TR(5, tt);
         if (h == h_end - 1) {            // every TMEM read of this warp from this accumulator buffer is done
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(map_to_cta(smem_u32(&tmem_empty[as]), 0), arrive_mode & 3);   // leader's barrier
+          if (warp == 2 && lane == 0) KTB_TR(6, tt);
         }
         fence_proxy_async_smem();
         if constexpr (WARP_STORE) {
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(arrive_mode & 8)) {   // bit 3: developer diagnostic (no stores), set through ktb_debug_set_ptr only
             const int r0 = quarter * 32;          // this warp's rows inside the CTA's 128
             tma_store_2d(&map_c32, ctile + (2 * h) * kBoxBytes + r0 * 128, n0 + 128 * h, m0 + r0);
             tma_store_2d(&map_c32, ctile + (2 * h + 1) * kBoxBytes + r0 * 128, n0 + 128 * h + 64, m0 + r0);
             bulk_commit();
+            if (warp == 2 && h == 1) KTB_TR(7, tt);
           }
         } else {
           epi_barrier_n<128>();
@@ -1015,16 +1145,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
         }
       }
     }
-    if (WARP_STORE ? (lane == 0) : issuer) bulk_wait_all<0>();
+    // shared memory must outlive the TMA engine's READS only; the writes complete with the grid (bit 4 of the mode
+    // restores the full completion wait: it held every CTA ~6 us at the end of the kernel, tools/probe_trace.py)
+    if (WARP_STORE ? (lane == 0) : issuer) { if (arrive_mode & 16) bulk_wait_all<0>(); else bulk_wait_read<0>(); }
+    }
   }
 
+  KTB_TG(2);
+  if (trace != nullptr && lane == 0) trace[2048 + blockIdx.x * 8 + warp] = globaltimer_ns();   // per-warp arrival at the end
   tc_fence_before();
-  cluster_sync_all();
+  if (arrive_mode & 32) cluster_sync_relaxed(); else cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, 2 * BLOCK_N);
   }
+  KTB_TG(3);
 }
+#undef KTB_TR
+#undef KTB_TG
 
 __device__ __forceinline__ void tma_load_2d_2sm_mc(void* smem_dst, const CUtensorMap* map, int c0, int c1,
                                                    uint32_t leader_bar_addr, uint16_t cta_mask) {
@@ -1240,7 +1378,7 @@ template <int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
     mlp_l2_head_fused_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                              const __grid_constant__ CUtensorMap map_w3, __nv_bfloat16* __restrict__ out, int ldo,
-                             int K, int tiles_m, int tiles_n, int arrive_mode) {
+                             int K, int tiles_m, int tiles_n, int arrive_mode, int pf_blocks) {
   constexpr int BLOCK_N = 256;
   constexpr int kABytes = kMlpBlockM * kMlpBlockK * 2;      // 16 KiB: this CTA's 128 rows of A
   constexpr int kBBytes = 128 * kMlpBlockK * 2;             // 16 KiB: this CTA's half of the W2 tile
@@ -1314,6 +1452,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
         const int m0 = unit * 256 + (int)rank * 128;
         const int n0 = (t % tiles_n) * BLOCK_N + (int)rank * 128;
         if (t == 0) load_w3(0);
+        if (pf_blocks > 0 && (t % tiles_n) == 1 && t / tiles_n + 1 < T / tiles_n) {
+          // L2 prefetch of the NEXT row block's h1 rows (read from HBM by its first n-tile, from L2 by the other three)
+          const int um0 = (unit + num_pairs) * 256 + (int)rank * 128;
+          for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_2d(&map_a, kb * kMlpBlockK, um0);
+        }
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait_bounded(&empty[s], ((it / STAGES) & 1) ^ 1);
@@ -1333,7 +1476,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
     }
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only) =====
-    if (leader && lane == 0) {
+    if (leader) {                     // whole warp, one elected lane issues (see elect_one_sync)
       constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N);
       constexpr uint32_t idesc3 = make_idesc_bf16(256, 64);
       auto issue_head = [&](int j) {   // logits partial of tile j into the first 64 columns of its drained buffer
@@ -1341,13 +1484,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
         mbar_wait_bounded(w3_full, (uint32_t)(j & 1));
         tc_fence_after();
         const uint32_t d3 = tmem_base + (uint32_t)((j & 1) * BLOCK_N);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < BLOCK_N / kMlpUmmaK; ++k) {
-          const uint64_t adesc = make_smem_desc_sw128(ctile + (k >> 2) * kBoxBytes) + (uint64_t)(2 * (k & 3));
-          const uint64_t bdesc = make_smem_desc_sw128(w3s + (k >> 2) * kW3Box) + (uint64_t)(2 * (k & 3));
-          umma_f16_2sm(d3, adesc, bdesc, idesc3, (uint32_t)(k != 0));
+          for (int k = 0; k < BLOCK_N / kMlpUmmaK; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(ctile + (k >> 2) * kBoxBytes) + (uint64_t)(2 * (k & 3));
+            const uint64_t bdesc = make_smem_desc_sw128(w3s + (k >> 2) * kW3Box) + (uint64_t)(2 * (k & 3));
+            umma_f16_2sm(d3, adesc, bdesc, idesc3, (uint32_t)(k != 0));
+          }
+          umma_commit_2sm(l3_full);
         }
-        umma_commit_2sm(l3_full);
+        __syncwarp();
       };
       int it = 0;
       for (int t = 0; t < T; ++t) {
@@ -1363,12 +1509,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
           const uint8_t* a_src = smem + (size_t)s * kStageBytes;
           const uint64_t adesc = make_smem_desc_sw128(a_src);
           const uint64_t bdesc = make_smem_desc_sw128(a_src + kABytes);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < kMlpBlockK / kMlpUmmaK; ++k)
-            umma_f16_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-          umma_commit_2sm(&empty[s]);
+            for (int k = 0; k < kMlpBlockK / kMlpUmmaK; ++k)
+              umma_f16_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            umma_commit_2sm(&empty[s]);
+            if (kb == num_kb - 1) umma_commit_2sm(&tmem_full[as]);
+          }
+          __syncwarp();
         }
-        umma_commit_2sm(&tmem_full[as]);
       }
       if (T >= 1) issue_head(T - 1);
     }
@@ -1617,24 +1766,33 @@ static int launch_gemm(int dev, const void* A, const void* B, void* C, size_t M,
       CUtensorMap mc32;
       rc = make_map(&mc32, C, M, (uint64_t)N, 32);      // per-warp stores: 64 columns x 32 rows
       if (rc) return rc;
-      if (g_mlp_l1_bres == 3) {
-        auto kfn = gemm_bf16_tn_2sm_bres_kernel<AST, RELU, true, 8>;
+      if (g_mlp_l1_bres == 4) {
+        constexpr int AST8 = 8;          // 2 tiles deep; C staging 32 KiB
+        constexpr int smem_l1q = AST8 * 16384 + 4 * 16384 + kMlpBlockM * 256 + (2 * AST8 + 5) * 8 + 16 + 1024;
+        static_assert(smem_l1q <= 232448, "the 8-stage layer-1 kernel must fit the opt-in shared memory limit");
+        auto kfn = gemm_bf16_tn_2sm_bres_kernel<AST8, RELU, 2>;
+        static std::atomic<unsigned> attr_done{0};
+        rc = ensure_smem_attr(kfn, smem_l1q, attr_done, dev);
+        if (rc) return rc;
+        kfn<<<grid, 64 + 128, smem_l1q, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n, g_mlp_arrive_mode | g_mlp_debug_flags, g_mlp_pf & 15, g_mlp_trace);
+      } else if (g_mlp_l1_bres == 3) {
+        auto kfn = gemm_bf16_tn_2sm_bres_kernel<AST, RELU, 1, 8>;
         static std::atomic<unsigned> attr_done{0};
         rc = ensure_smem_attr(kfn, smem_l1, attr_done, dev);
         if (rc) return rc;
-        kfn<<<grid, 64 + 256, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n, g_mlp_arrive_mode);
+        kfn<<<grid, 64 + 256, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n, g_mlp_arrive_mode | g_mlp_debug_flags, g_mlp_pf & 15, g_mlp_trace);
       } else if (g_mlp_l1_bres == 2) {
-        auto kfn = gemm_bf16_tn_2sm_bres_kernel<AST, RELU, true>;
+        auto kfn = gemm_bf16_tn_2sm_bres_kernel<AST, RELU, 1>;
         static std::atomic<unsigned> attr_done{0};
         rc = ensure_smem_attr(kfn, smem_l1, attr_done, dev);
         if (rc) return rc;
-        kfn<<<grid, 64 + 128, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n, g_mlp_arrive_mode);
+        kfn<<<grid, 64 + 128, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n, g_mlp_arrive_mode | g_mlp_debug_flags, g_mlp_pf & 15, g_mlp_trace);
       } else {
-        auto kfn = gemm_bf16_tn_2sm_bres_kernel<AST, RELU, false>;
+        auto kfn = gemm_bf16_tn_2sm_bres_kernel<AST, RELU, 0>;
         static std::atomic<unsigned> attr_done{0};
         rc = ensure_smem_attr(kfn, smem_l1, attr_done, dev);
         if (rc) return rc;
-        kfn<<<grid, 64 + 128, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n, g_mlp_arrive_mode);
+        kfn<<<grid, 64 + 128, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n, g_mlp_arrive_mode | g_mlp_debug_flags, g_mlp_pf & 15, g_mlp_trace);
       }
       KTB_CK(cudaGetLastError());
       return KTB_OK;
@@ -1740,7 +1898,7 @@ static int launch_l2_head_fused(int dev, const void* h1, const void* W2, const v
   const int sms = device_info(dev) ? device_info(dev)->sm_count : 148;
   const int grid = 2 * std::max(1, std::min(tiles_m, sms / 2));
   kfn<<<grid, 64 + 128, smem_bytes, stream>>>(ma, mb, mw3, static_cast<__nv_bfloat16*>(logits), d_out, d_hidden, tiles_m,
-                                              tiles_n, g_mlp_arrive_mode);
+                                              tiles_n, g_mlp_arrive_mode, g_mlp_pf >> 4);
   KTB_CK(cudaGetLastError());
   return KTB_OK;
 }
@@ -1749,6 +1907,13 @@ static int launch_l2_head_fused(int dev, const void* h1, const void* W2, const v
 using namespace ktb;
 
 extern "C" {
+
+// Developer hook (not part of include/ktb200.h): key 0 = trace buffer of the layer-1 kernel, NULL switches it off.
+int ktb_debug_set_ptr(int key, void* p) {
+  if (key == 0) { g_mlp_trace = static_cast<unsigned long long*>(p); return KTB_OK; }
+  if (key == 1) { g_mlp_debug_flags = (int)(reinterpret_cast<uintptr_t>(p) & 8); return KTB_OK; }
+  return KTB_ERR_ARG;
+}
 
 size_t ktb_mlp_scratch_bytes(size_t M, int d_hidden) {
   const size_t rows = std::min<size_t>(M, (size_t)g_mlp_chunk_rows);

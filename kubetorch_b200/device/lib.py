@@ -95,6 +95,7 @@ _SIGNATURES = {
                                     c_uintptr]),
     # experiment knob, not in the stable header
     "ktb_set_tuning": (c_int, [c_int, c_int]),
+    "ktb_debug_set_ptr": (c_int, [c_int, c_void_p]),
 }
 
 _lib = None

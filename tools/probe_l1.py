@@ -20,7 +20,7 @@ w3 = (torch.randn(64, 1024, device="cuda", generator=g) * 0.02).bfloat16()
 def run(rows, iters=10):
     obs = torch.randn(rows, 256, device="cuda", generator=g).bfloat16()
     out = {}
-    for flag in (0, 1, 2, 3):
+    for flag in (0, 1, 2, 3, 4):
         ops.set_tuning(24, flag)
         y = mlp.mlp_forward(obs, w1, w2, w3)
         torch.cuda.synchronize()
@@ -36,9 +36,9 @@ def run(rows, iters=10):
         ms = a.elapsed_time(b) / iters
         out[flag] = (y.clone(), ms)
     ops.set_tuning(24, 2)
-    same = bool(torch.equal(out[0][0], out[1][0])) and bool(torch.equal(out[0][0], out[2][0])) and bool(torch.equal(out[0][0], out[3][0]))
+    same = bool(torch.equal(out[0][0], out[1][0])) and bool(torch.equal(out[0][0], out[2][0])) and bool(torch.equal(out[0][0], out[3][0])) and bool(torch.equal(out[0][0], out[4][0]))
     flop = 2 * (256 * 1024 + 1024 * 1024 + 1024 * 64) * rows
-    print(json.dumps({"rows": rows, "bit_identical": same, "ms_pair_kernel": out[0][1], "ms_bres_kernel": out[1][1], "ms_warp_store": out[2][1], "ms_warp_store_8w": out[3][1], "tflops_8w": flop / out[3][1] / 1e9, "tflops_warp_store": flop / out[2][1] / 1e9,
+    print(json.dumps({"rows": rows, "bit_identical": same, "ms_pair_kernel": out[0][1], "ms_bres_kernel": out[1][1], "ms_warp_store": out[2][1], "ms_warp_store_8w": out[3][1], "ms_quarter_boxes_8st": out[4][1], "tflops_quarter_boxes_8st": flop / out[4][1] / 1e9, "tflops_8w": flop / out[3][1] / 1e9, "tflops_warp_store": flop / out[2][1] / 1e9,
                       "tflops_pair": flop / out[0][1] / 1e9, "tflops_bres": flop / out[1][1] / 1e9}), flush=True)
     return same
 

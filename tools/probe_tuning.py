@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Epilogue hand-back semantics (ktb_set_tuning(25, mode)) for the layer-1 and the fused layer-2+head kernels:
+"""Generic MLP tuning probe: ktb_set_tuning(KEY, mode) for KEY, MODES from argv (default key 25).
+Epilogue hand-back semantics (ktb_set_tuning(25, mode)) for the layer-1 and the fused layer-2+head kernels:
 bit-identity against mode 0 and time.  mode & 3: 0 = release.cluster arrives, 1 = CTA-scope release for the TMEM
 hand-backs, 2 = also for c_ready; mode & 4: software-pipelined TMEM loads in the fused kernel's epilogue."""
 import json
@@ -17,14 +18,16 @@ g = torch.Generator(device="cuda").manual_seed(0)
 w1 = (torch.randn(1024, 256, device="cuda", generator=g) * 0.02).bfloat16()
 w2 = (torch.randn(1024, 1024, device="cuda", generator=g) * 0.02).bfloat16()
 w3 = (torch.randn(64, 1024, device="cuda", generator=g) * 0.02).bfloat16()
-MODES = (0, 1, 2, 5, 6)
+KEY = int(sys.argv[1]) if len(sys.argv) > 1 else 25
+MODES = tuple(int(v) for v in sys.argv[2].split(",")) if len(sys.argv) > 2 else (0, 1, 2, 5, 6)
+RESET = int(sys.argv[3]) if len(sys.argv) > 3 else MODES[0]
 
 
 def run(rows, iters=10, reps=3):
     obs = torch.randn(rows, 256, device="cuda", generator=g).bfloat16()
     out = {}
     for mode in MODES:
-        ops.set_tuning(25, mode)
+        ops.set_tuning(KEY, mode)
         y = mlp.mlp_forward(obs, w1, w2, w3)
         torch.cuda.synchronize()
         for _ in range(3):
@@ -40,8 +43,8 @@ def run(rows, iters=10, reps=3):
             torch.cuda.synchronize()
             best = min(best, a.elapsed_time(b) / iters)
         out[mode] = (y.clone(), best)
-    ops.set_tuning(25, 0)
-    same = all(bool(torch.equal(out[0][0], out[m][0])) for m in MODES)
+    ops.set_tuning(KEY, RESET)
+    same = all(bool(torch.equal(out[MODES[0]][0], out[m][0])) for m in MODES)
     flop = 2 * (256 * 1024 + 1024 * 1024 + 1024 * 64) * rows
     print(json.dumps({"rows": rows, "bit_identical": same,
                       "ms": {str(m): round(out[m][1], 5) for m in MODES},
