@@ -34,7 +34,6 @@ extern int g_mlp_tma_store;    // ktb_mlp.cu
 extern int g_mlp_2sm;          // ktb_mlp.cu
 extern int g_mlp_l1_bres;      // ktb_mlp.cu
 extern int g_mlp_arrive_mode;  // ktb_mlp.cu
-extern int g_mlp_pf;           // ktb_mlp.cu
 }  // namespace ktb
 extern int g_mlp_stage_ce;     // ktb_mlp.cu (file scope there)
 namespace ktb {
@@ -386,7 +385,6 @@ int ktb_set_tuning(int key, int value) {
     case 14: g_red_fold = value ? 1 : 0; return KTB_OK;
     case 18: g_mlp_fuse_head = value ? 1 : 0; return KTB_OK;
     case 20: g_host_zero_copy = value ? 1 : 0; return KTB_OK;
-    case 26: g_mlp_pf = (value >= 0 && value <= 31) ? value : 0; return KTB_OK;
     case 25: g_mlp_arrive_mode = (value >= 0 && value <= 63 && (value & 3) != 3 && !(value & 8)) ? value : 1; return KTB_OK;   // bit 2: pipelined TMEM loads in the fused epilogue
     case 24: g_mlp_l1_bres = (value >= 0 && value <= 4) ? value : 2; return KTB_OK;   // 2 = per-warp stores, 3 = + 8 epilogue warps
     case 23: g_push_slice = value > 0 ? value : 1; return KTB_OK;

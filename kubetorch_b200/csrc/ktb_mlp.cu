@@ -40,8 +40,6 @@ int g_mlp_stages = 4;          // ktb_set_tuning key 17: TMA ring depth of the C
 int g_mlp_cluster4 = 0;        // ktb_set_tuning key 15: 1 = cluster-of-4 multicast form of the CTA-pair kernel (opt-in)
 unsigned long long* g_mlp_trace = nullptr;   // ktb_debug_set_ptr(0, p): device buffer of 16 x 64 clock64() stamps (layer-1 kernel)
 int g_mlp_debug_flags = 0;     // ktb_debug_set_ptr(1, flags): bit 3 = layer-1 kernel issues no TMA stores (timing diagnostic, wrong results)
-int g_mlp_pf = 0;              // ktb_set_tuning key 26: low 4 bits = L2 prefetch distance (tiles) of the layer-1 kernel's A operand,
-                               // bit 4 = prefetch the next row block's h1 in the fused kernel
 int g_mlp_arrive_mode = 1;     // ktb_set_tuning key 25: semantics of the epilogue's remote mbarrier arrives (see mbar_arrive_remote):
                                // 0 = release.cluster everywhere, 1 = CTA-scope release for the TMEM hand-backs (default: +6 %,
                                // profiles/r2n_probe_arrive.log), 2 = also for c_ready; bit 2 = pipelined TMEM loads in the fused epilogue
@@ -399,6 +397,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_2d_s(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync %0, 128;" ::"n"(kEpiBarrier) : "memory"); }
 template <int NTHREADS>
 __device__ __forceinline__ void epi_barrier_n() {
@@ -594,6 +597,15 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr, int ct
   else
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// two fp32 -> packed bf16 (round to nearest even), then ReLU on the PACKED pair (one HMNMX2 for two values instead of
+// two FMNMX: the epilogue warps are ALU-bound).  Same bits as rounding relu(x): rounding is monotonic and keeps the sign,
+// max(-0, +0) = +0 and max(NaN, 0) = 0 in both forms.
+template <bool RELU>
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  if (RELU) v = __hmax2(v, __floats2bfloat162_rn(0.f, 0.f));
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -624,10 +636,6 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
           "r"(smem_u32(smem_dst)),
       "l"(map), "r"(leader_bar_addr), "r"(c0), "r"(c1)
       : "memory");
-}
-// L2 prefetch of one TMA box (no shared memory, no barrier): the later cp.async.bulk.tensor of the same box hits L2
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
@@ -839,8 +847,7 @@ template <int AST, bool RELU, int STORE, int EPI_WARPS = 4>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS, 1)
     gemm_bf16_tn_2sm_bres_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                  const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c32,
-                                 int tiles_m, int tiles_n, int arrive_mode, int pf_tiles,
-                                 unsigned long long* trace) {
+                                 int tiles_m, int tiles_n, int arrive_mode, unsigned long long* trace) {
   // trace (developer tool, tools/probe_trace.py; nullptr in every product call): the leader CTA of pair 0 records
   // clock64() at the hand-offs of its first 64 tiles, trace[event * 64 + tile]
 #define KTB_TR(ev, tile) \
@@ -870,7 +877,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
   uint64_t* b_full = tmem_empty + 2;                                // [1], used on the leader only
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(b_full + 1);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: provably warp-uniform for the compiler (uniform branches, uniform-register operands)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = (rank == 0);
@@ -908,40 +916,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs) =====
-    if (lane == 0) {
+    {                                 // whole warp walks the loop, one elected lane issues (see elect_one_sync)
       int it = 0, cur_n = -1;
       for (int t = t_begin; t < t_end; ++t) {
         const int n = t / tiles_m;
         const int m0 = (t % tiles_m) * 256 + (int)rank * 128;
-        KTB_TR(8, t - t_begin);
-        if (pf_tiles > 0) {
-          // the A tiles stream from HBM once, under 3.5 TB/s of h1 writes: a TMA load takes ~1.9 us from issue to
-          // barrier (tools/probe_trace.py), longer than the 1.5-tile ring covers; an L2 prefetch pf_tiles ahead hides it
-          const int first = (t == t_begin) ? t + 1 : t + pf_tiles;
-          for (int u = first; u <= t + pf_tiles && u < t_end; ++u) {
-            const int um0 = (u % tiles_m) * 256 + (int)rank * 128;
-#pragma unroll
-            for (int kb = 0; kb < KB; ++kb) tma_prefetch_2d(&map_a, kb * kMlpBlockK, um0);
-          }
-        }
+        if (lane == 0) KTB_TR(8, t - t_begin);
         if (n != cur_n) {
           // every MMA that reads the resident B has retired once the commit of the previous tile's last k-block arrived
           if (it > 0) mbar_wait_bounded(&empty[(it - 1) % AST], ((it - 1) / AST) & 1);
-          if (leader) mbar_expect_tx(b_full, 2 * KB * kBBytes);
           const uint32_t leader_b_full = smem_u32(b_full) & 0xFEFFFFFFu;
           const int n0 = n * BLOCK_N + (int)rank * 128;
+          if (elect_one_sync()) {
+            if (leader) mbar_expect_tx(b_full, 2 * KB * kBBytes);
 #pragma unroll
-          for (int kb = 0; kb < KB; ++kb) tma_load_2d_2sm(b_res + kb * kBBytes, &map_b, kb * kMlpBlockK, n0, leader_b_full);
+            for (int kb = 0; kb < KB; ++kb) tma_load_2d_2sm(b_res + kb * kBBytes, &map_b, kb * kMlpBlockK, n0, leader_b_full);
+          }
+          __syncwarp();
           cur_n = n;
         }
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % AST;
           mbar_wait_bounded(&empty[s], ((it / AST) & 1) ^ 1);
-          if (leader) mbar_expect_tx(&full[s], 2 * kABytes);
           const uint32_t leader_full_tma = smem_u32(&full[s]) & 0xFEFFFFFFu;
-          tma_load_2d_2sm(a_ring + (size_t)s * kABytes, &map_a, kb * kMlpBlockK, m0, leader_full_tma);
+          if (elect_one_sync()) {
+            if (leader) mbar_expect_tx(&full[s], 2 * kABytes);
+            tma_load_2d_2sm(a_ring + (size_t)s * kABytes, &map_a, kb * kMlpBlockK, m0, leader_full_tma);
+          }
+          __syncwarp();
         }
-        KTB_TR(9, t - t_begin);
+        if (lane == 0) KTB_TR(9, t - t_begin);
       }
     }
   } else if (warp == 1) {
@@ -1005,14 +1009,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
         uint32_t pk[4];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-          float lo = __uint_as_float(acc[8 * q + 2 * jj]);
-          float hi = __uint_as_float(acc[8 * q + 2 * jj + 1]);
-          if (RELU) {
-            lo = fmaxf(lo, 0.f);
-            hi = fmaxf(hi, 0.f);
-          }
-          __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-          pk[jj] = *reinterpret_cast<uint32_t*>(&v);
+          pk[jj] = pack_bf16x2_relu<RELU>(__uint_as_float(acc[8 * q + 2 * jj]), __uint_as_float(acc[8 * q + 2 * jj + 1]));
         }
         const int phys = (chunk0 + q) ^ (row & 7);
         st_shared_v4(box + (uint32_t)(phys * 16), pk[0], pk[1], pk[2], pk[3]);     // STS.128, not a generic store
@@ -1028,14 +1025,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
           uint32_t pk[4];
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
-            float lo = __uint_as_float(acc[8 * q + 2 * jj]);
-            float hi = __uint_as_float(acc[8 * q + 2 * jj + 1]);
-            if (RELU) {
-              lo = fmaxf(lo, 0.f);
-              hi = fmaxf(hi, 0.f);
-            }
-            __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-            pk[jj] = *reinterpret_cast<uint32_t*>(&v);
+            pk[jj] = pack_bf16x2_relu<RELU>(__uint_as_float(acc[8 * q + 2 * jj]), __uint_as_float(acc[8 * q + 2 * jj + 1]));
           }
           const int phys = (chunk0 + q) ^ (lane & 7);
           st_shared_v4(boxrow + (uint32_t)(phys * 16), pk[0], pk[1], pk[2], pk[3]);
@@ -1053,7 +1043,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
         tmem_ld_32x32b_x32_nowait(tbase, acc0);
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
-          if (lane == 0) bulk_wait_read<1>();
+          bulk_wait_read<1>();
           __syncwarp();
           const uint32_t boxrow = cwarp + (uint32_t)((g & 1) * 4096);
           tmem_wait_ld();
@@ -1070,14 +1060,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && !(arrive_mode & 8)) {
-            tma_store_2d(&map_c32, ctile + quarter * 8192 + (g & 1) * 4096, n0 + 64 * g, m0);
-            bulk_commit();
-            if (warp == 2 && g == 3) KTB_TR(7, tt);
+          if (!(arrive_mode & 8)) {
+            const uint32_t src = ctile_s + (uint32_t)(quarter * 8192 + (g & 1) * 4096);
+            if (elect_one_sync()) {
+              tma_store_2d_s(&map_c32, src, n0 + 64 * g, m0);
+              bulk_commit();
+            }
+            __syncwarp();
           }
+          if (warp == 2 && lane == 0 && g == 3) KTB_TR(7, tt);
         }
       }
-      if (lane == 0) { if (arrive_mode & 16) bulk_wait_all<0>(); else bulk_wait_read<0>(); }
+      if (arrive_mode & 16) bulk_wait_all<0>(); else bulk_wait_read<0>();
     } else {
     for (int t = t_begin; t < t_end; ++t, ++tt) {
       const int as = tt & 1;
@@ -1098,9 +1092,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
         if constexpr (WARP_STORE) {
           // every epilogue warp owns its 32 rows end to end (own bulk groups, own TMA stores of 64 x 32 boxes): no
           // CTA-wide barrier in the epilogue, a slow warp delays nobody
-          if (lane == 0) {
-            if constexpr (EPI_WARPS == 8) bulk_wait_read<0>(); else bulk_wait_read<1>();
-          }
+          // every lane executes the wait (only the elected issuer owns bulk groups; elect.sync picks the same lane for
+          // the same member mask every time), then the warp re-converges
+          if constexpr (EPI_WARPS == 8) bulk_wait_read<0>(); else bulk_wait_read<1>();
           __syncwarp();
           if (warp == 2 && lane == 0) KTB_TR(10 + h, tt);
         } else {
@@ -1128,13 +1122,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
         fence_proxy_async_smem();
         if constexpr (WARP_STORE) {
           __syncwarp();
-          if (lane == 0 && !(arrive_mode & 8)) {   // bit 3: developer diagnostic (no stores), set through ktb_debug_set_ptr only
-            const int r0 = quarter * 32;          // this warp's rows inside the CTA's 128
-            tma_store_2d(&map_c32, ctile + (2 * h) * kBoxBytes + r0 * 128, n0 + 128 * h, m0 + r0);
-            tma_store_2d(&map_c32, ctile + (2 * h + 1) * kBoxBytes + r0 * 128, n0 + 128 * h + 64, m0 + r0);
-            bulk_commit();
-            if (warp == 2 && h == 1) KTB_TR(7, tt);
+          // operands computed by the whole warp (uniform registers), issued by lane 0, which owns the bulk groups
+          const int r0 = quarter * 32;            // this warp's rows inside the CTA's 128
+          const uint32_t src0 = ctile_s + (uint32_t)((2 * h) * kBoxBytes + r0 * 128);
+          const int sc0 = n0 + 128 * h, sc1 = m0 + r0;
+          if (!(arrive_mode & 8)) {                // bit 3: developer diagnostic (no stores), set through ktb_debug_set_ptr only
+            if (elect_one_sync()) {                // one active lane: plain uniform-register operands, no waterfall loop
+              tma_store_2d_s(&map_c32, src0, sc0, sc1);
+              tma_store_2d_s(&map_c32, src0 + (uint32_t)kBoxBytes, sc0 + 64, sc1);
+              bulk_commit();
+            }
+            __syncwarp();
           }
+          if (warp == 2 && lane == 0 && h == 1) KTB_TR(7, tt);
         } else {
           epi_barrier_n<128>();
           if (issuer) {
@@ -1147,7 +1147,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS,
     }
     // shared memory must outlive the TMA engine's READS only; the writes complete with the grid (bit 4 of the mode
     // restores the full completion wait: it held every CTA ~6 us at the end of the kernel, tools/probe_trace.py)
-    if (WARP_STORE ? (lane == 0) : issuer) { if (arrive_mode & 16) bulk_wait_all<0>(); else bulk_wait_read<0>(); }
+    if (WARP_STORE || issuer) { if (arrive_mode & 16) bulk_wait_all<0>(); else bulk_wait_read<0>(); }
     }
   }
 
@@ -1378,7 +1378,7 @@ template <int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
     mlp_l2_head_fused_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                              const __grid_constant__ CUtensorMap map_w3, __nv_bfloat16* __restrict__ out, int ldo,
-                             int K, int tiles_m, int tiles_n, int arrive_mode, int pf_blocks) {
+                             int K, int tiles_m, int tiles_n, int arrive_mode) {
   constexpr int BLOCK_N = 256;
   constexpr int kABytes = kMlpBlockM * kMlpBlockK * 2;      // 16 KiB: this CTA's 128 rows of A
   constexpr int kBBytes = 128 * kMlpBlockK * 2;             // 16 KiB: this CTA's half of the W2 tile
@@ -1400,7 +1400,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
   uint64_t* w3_full = l3_full + 1;                                  // leader only
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w3_full + 1);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: provably warp-uniform for the compiler (uniform branches, uniform-register operands)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = (rank == 0);
@@ -1437,14 +1438,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs) =====
-    if (lane == 0) {
+    {                                 // whole warp walks the loop, one elected lane issues (see elect_one_sync)
       const uint32_t leader_w3 = smem_u32(w3_full) & 0xFEFFFFFFu;
       auto load_w3 = [&](int t) {      // this CTA's 32 rows of W3[:, tn*256 : tn*256+256]
         const int tn = t % tiles_n;
-        if (leader) mbar_expect_tx(w3_full, 2 * kW3Bytes);
+        if (elect_one_sync()) {
+          if (leader) mbar_expect_tx(w3_full, 2 * kW3Bytes);
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
-          tma_load_2d_2sm(w3s + b * kW3Box, &map_w3, tn * BLOCK_N + 64 * b, (int)rank * 32, leader_w3);
+          for (int b = 0; b < 4; ++b)
+            tma_load_2d_2sm(w3s + b * kW3Box, &map_w3, tn * BLOCK_N + 64 * b, (int)rank * 32, leader_w3);
+        }
+        __syncwarp();
       };
       int it = 0;
       for (int t = 0; t < T; ++t) {
@@ -1452,19 +1456,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
         const int m0 = unit * 256 + (int)rank * 128;
         const int n0 = (t % tiles_n) * BLOCK_N + (int)rank * 128;
         if (t == 0) load_w3(0);
-        if (pf_blocks > 0 && (t % tiles_n) == 1 && t / tiles_n + 1 < T / tiles_n) {
-          // L2 prefetch of the NEXT row block's h1 rows (read from HBM by its first n-tile, from L2 by the other three)
-          const int um0 = (unit + num_pairs) * 256 + (int)rank * 128;
-          for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_2d(&map_a, kb * kMlpBlockK, um0);
-        }
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait_bounded(&empty[s], ((it / STAGES) & 1) ^ 1);
           uint8_t* a_dst = smem + (size_t)s * kStageBytes;
-          if (leader) mbar_expect_tx(&full[s], 2 * kStageBytes);
           const uint32_t leader_full_tma = smem_u32(&full[s]) & 0xFEFFFFFFu;
-          tma_load_2d_2sm(a_dst, &map_a, kb * kMlpBlockK, m0, leader_full_tma);
-          tma_load_2d_2sm(a_dst + kABytes, &map_b, kb * kMlpBlockK, n0, leader_full_tma);
+          if (elect_one_sync()) {
+            if (leader) mbar_expect_tx(&full[s], 2 * kStageBytes);
+            tma_load_2d_2sm(a_dst, &map_a, kb * kMlpBlockK, m0, leader_full_tma);
+            tma_load_2d_2sm(a_dst + kABytes, &map_b, kb * kMlpBlockK, n0, leader_full_tma);
+          }
+          __syncwarp();
         }
         if (t >= 1) {
           // the W3 buffer is free once the head MMA of tile t-1 has completed; that MMA is issued in the middle of
@@ -1545,10 +1547,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128)
           uint32_t pk[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float lo = fmaxf(__uint_as_float(acc[8 * q + 2 * j]), 0.f);
-            const float hi = fmaxf(__uint_as_float(acc[8 * q + 2 * j + 1]), 0.f);
-            __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-            pk[j] = *reinterpret_cast<uint32_t*>(&v);
+            pk[j] = pack_bf16x2_relu<true>(__uint_as_float(acc[8 * q + 2 * j]), __uint_as_float(acc[8 * q + 2 * j + 1]));
           }
           const int phys = (chunk0 + q) ^ (row & 7);
           st_shared_v4(box + (uint32_t)(phys * 16), pk[0], pk[1], pk[2], pk[3]);
@@ -1774,25 +1773,25 @@ static int launch_gemm(int dev, const void* A, const void* B, void* C, size_t M,
         static std::atomic<unsigned> attr_done{0};
         rc = ensure_smem_attr(kfn, smem_l1q, attr_done, dev);
         if (rc) return rc;
-        kfn<<<grid, 64 + 128, smem_l1q, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n, g_mlp_arrive_mode | g_mlp_debug_flags, g_mlp_pf & 15, g_mlp_trace);
+        kfn<<<grid, 64 + 128, smem_l1q, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n, g_mlp_arrive_mode | g_mlp_debug_flags, g_mlp_trace);
       } else if (g_mlp_l1_bres == 3) {
         auto kfn = gemm_bf16_tn_2sm_bres_kernel<AST, RELU, 1, 8>;
         static std::atomic<unsigned> attr_done{0};
         rc = ensure_smem_attr(kfn, smem_l1, attr_done, dev);
         if (rc) return rc;
-        kfn<<<grid, 64 + 256, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n, g_mlp_arrive_mode | g_mlp_debug_flags, g_mlp_pf & 15, g_mlp_trace);
+        kfn<<<grid, 64 + 256, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n, g_mlp_arrive_mode | g_mlp_debug_flags, g_mlp_trace);
       } else if (g_mlp_l1_bres == 2) {
         auto kfn = gemm_bf16_tn_2sm_bres_kernel<AST, RELU, 1>;
         static std::atomic<unsigned> attr_done{0};
         rc = ensure_smem_attr(kfn, smem_l1, attr_done, dev);
         if (rc) return rc;
-        kfn<<<grid, 64 + 128, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n, g_mlp_arrive_mode | g_mlp_debug_flags, g_mlp_pf & 15, g_mlp_trace);
+        kfn<<<grid, 64 + 128, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n, g_mlp_arrive_mode | g_mlp_debug_flags, g_mlp_trace);
       } else {
         auto kfn = gemm_bf16_tn_2sm_bres_kernel<AST, RELU, 0>;
         static std::atomic<unsigned> attr_done{0};
         rc = ensure_smem_attr(kfn, smem_l1, attr_done, dev);
         if (rc) return rc;
-        kfn<<<grid, 64 + 128, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n, g_mlp_arrive_mode | g_mlp_debug_flags, g_mlp_pf & 15, g_mlp_trace);
+        kfn<<<grid, 64 + 128, smem_l1, stream>>>(ma, mb2, mc, mc32, tiles_m, tiles_n, g_mlp_arrive_mode | g_mlp_debug_flags, g_mlp_trace);
       }
       KTB_CK(cudaGetLastError());
       return KTB_OK;
@@ -1898,7 +1897,7 @@ static int launch_l2_head_fused(int dev, const void* h1, const void* W2, const v
   const int sms = device_info(dev) ? device_info(dev)->sm_count : 148;
   const int grid = 2 * std::max(1, std::min(tiles_m, sms / 2));
   kfn<<<grid, 64 + 128, smem_bytes, stream>>>(ma, mb, mw3, static_cast<__nv_bfloat16*>(logits), d_out, d_hidden, tiles_m,
-                                              tiles_n, g_mlp_arrive_mode, g_mlp_pf >> 4);
+                                              tiles_n, g_mlp_arrive_mode);
   KTB_CK(cudaGetLastError());
   return KTB_OK;
 }

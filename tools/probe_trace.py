@@ -22,8 +22,6 @@ w2 = (torch.randn(1024, 1024, device="cuda", generator=g) * 0.02).bfloat16()
 w3 = (torch.randn(64, 1024, device="cuda", generator=g) * 0.02).bfloat16()
 obs = torch.randn(rows, 256, device="cuda", generator=g).bfloat16()
 ops.set_tuning(24, variant)
-if len(sys.argv) > 3:
-    ops.set_tuning(26, int(sys.argv[3]))
 if len(sys.argv) > 5:
     ops.set_tuning(25, int(sys.argv[5]))
 if len(sys.argv) > 4:
