@@ -342,7 +342,7 @@ def test_mlp_tcgen05_matches_recorded_reference_and_fp32(K, golden):
         K.set_tuning(9, 1)
         K.set_tuning(24, 0)  # layer 1 through the generic pair kernel instead of its K = 256 form: same bits
         assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got2)
-        for v in (1, 3):     # layer-1 kernel with CTA-wide stores / with eight epilogue warps: same bits
+        for v in (1, 3, 4):  # layer-1 kernel with CTA-wide stores / eight epilogue warps / 8-stage ring + quarter boxes
             K.set_tuning(24, v)
             assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got2)
         K.set_tuning(24, 2)
@@ -365,6 +365,10 @@ def test_mlp_tcgen05_matches_recorded_reference_and_fp32(K, golden):
     K.set_tuning(24, 0)   # the fused default with layer 1 on the generic pair kernel: same bits as the shipped default
     assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got_fused)
     K.set_tuning(24, 2)
+    for mode in (0, 2, 6, 33):   # hand-back arrive semantics / pipelined TMEM loads / relaxed final cluster barrier: same bits
+        K.set_tuning(25, mode)
+        assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got_fused)
+    K.set_tuning(25, 1)
     K.set_tuning(8, 4096)
     try:
         assert torch.equal(mlp.mlp_forward(obs2.cuda(), w1, w2, w3).cpu().float(), got_fused)
