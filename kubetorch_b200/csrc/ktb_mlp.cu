@@ -697,7 +697,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * EPI_GROUP
   uint64_t* tmem_empty = tmem_full + 2;                             // [2], used on the leader only
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform (see the layer-1 kernel)
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = (rank == 0);
@@ -730,7 +730,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * EPI_GROUP
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs) =====
-    if (lane == 0) {
+    {                                 // whole warp walks the loop, one elected lane issues (see elect_one_sync)
       int it = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int m0 = (tile / tiles_n) * 256 + (int)rank * 128;
@@ -742,16 +742,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * EPI_GROUP
           // The leader expects the bytes of all four loads of this k-block (its own two and the peer's two); the
           // peer's complete_tx may land first (the tx-count goes transiently negative, the phase cannot complete
           // before the leader's arrive).  No remote arrive sits on the peer's critical path.
-          if (leader) mbar_expect_tx(&full[s], 2 * kStageBytes);
           const uint32_t leader_full_tma = smem_u32(&full[s]) & 0xFEFFFFFFu;   // peer bit cleared → CTA 0's barrier
-          tma_load_2d_2sm(a_dst, &map_a, kb * kMlpBlockK, m0, leader_full_tma);
-          tma_load_2d_2sm(a_dst + kABytes, &map_b, kb * kMlpBlockK, n0, leader_full_tma);
+          if (elect_one_sync()) {
+            if (leader) mbar_expect_tx(&full[s], 2 * kStageBytes);
+            tma_load_2d_2sm(a_dst, &map_a, kb * kMlpBlockK, m0, leader_full_tma);
+            tma_load_2d_2sm(a_dst + kABytes, &map_b, kb * kMlpBlockK, n0, leader_full_tma);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only) =====
-    if (leader && lane == 0) {
+    if (leader) {                     // whole warp, one elected lane issues
       constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N);
       int it = 0, t = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++t) {
@@ -766,12 +769,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * EPI_GROUP
           const uint8_t* a_src = smem + (size_t)s * kStageBytes;
           const uint64_t adesc = make_smem_desc_sw128(a_src);
           const uint64_t bdesc = make_smem_desc_sw128(a_src + kABytes);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < kMlpBlockK / kMlpUmmaK; ++k)
-            umma_f16_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-          umma_commit_2sm(&empty[s]);          // stage free in both CTAs
+            for (int k = 0; k < kMlpBlockK / kMlpUmmaK; ++k)
+              umma_f16_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            umma_commit_2sm(&empty[s]);          // stage free in both CTAs
+            if (kb == num_kb - 1) umma_commit_2sm(&tmem_full[as]);       // accumulator ready in both CTAs
+          }
+          __syncwarp();
         }
-        umma_commit_2sm(&tmem_full[as]);       // accumulator ready in both CTAs
       }
     }
   } else {
@@ -816,7 +822,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * EPI_GROUP
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));   // leader's barrier
+      if (lane == 0) mbar_arrive_remote(map_to_cta(smem_u32(&tmem_empty[as]), 0), 1);   // leader's barrier, CTA-scope release
       fence_proxy_async_smem();
       epi_barrier_n<128 * EPI_GROUPS>();
       if (issuer) {
