@@ -35,6 +35,25 @@ def test_library_is_sm100a_only():
     assert archs == {"100a"}, archs
 
 
+def test_mlp_kernels_issue_tcgen05_and_tma_without_waterfall_loops():
+    """The shipped MLP kernels (layer-1 form, generic CTA-pair kernel, fused layer 2 + head) are tcgen05 / TMA kernels whose
+    single-lane instructions are issued from converged warps through elect.sync: no UTCHMMA / UTMALDG / UTMASTG sits in
+    an ELECT + R2UR.BROADCAST + BRA.U.ANY loop (that form issued one MMA per ~177 cycles instead of 128)."""
+    import subprocess
+
+    sass = subprocess.run(["cuobjdump", "-sass", L.lib_path()], capture_output=True, text=True).stdout
+    funcs = sass.split("Function : ")[1:]
+    wanted = {"gemm_bf16_tn_2sm_bres_kernel": 0, "gemm_bf16_tn_2sm_kernel": 0, "mlp_l2_head_fused_kernel": 0}
+    for f in funcs:
+        name = f.split("\n", 1)[0]
+        for key in wanted:
+            if key + "I" in name:          # mangled: <name>I<template args>
+                wanted[key] += 1
+                assert "UTCHMMA.2CTA" in f and "UTMALDG" in f and "LDTM" in f, name
+                assert "BRA.U.ANY" not in f, name      # the loop-back branch of the waterfall
+    assert all(v >= 1 for v in wanted.values()), wanted
+
+
 @pytest.mark.parametrize("n,world", [(0, 1), (1, 4), (3, 4), (5, 4), (1003, 4), (1000, 3), (64, 8), (2**26, 8), (7, 7)])
 def test_shard_bounds_equal_torch_chunk(n, world):
     x = torch.arange(n)
