@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Hand-off timeline of the layer-1 kernel (pair 0, leader CTA): clock64() stamps per tile, printed relative to the
-first stamp in microseconds (SM clock taken from nvidia-smi at the time)."""
+first stamp in microseconds AT THE NOMINAL CLOCK nvidia-smi reports after the run (under the power cap the real SM clock
+inside the kernel is lower: compare with the per-CTA globaltimer stamps printed below).
+usage: probe_trace.py [rows=75776] [layer-1 variant (tuning 24)=2] [-] [debug flags: 8 = no TMA stores] [tuning 25 value]"""
 import json
 import os
 import subprocess
